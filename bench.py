@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native Gaussian rasterizer (BASELINE.json metric).
+
+Metric: forward+backward frames/s at 1M Gaussians, 640x480 (config "C-main").
+A *step* is one 8-keyframe mapping step: every keyframe gets one rasterizer forward + backward
+(SH path, fixed random dL/dpix), parameter gradients accumulate into one flat bucket, and with
+N > 1 GPUs the keyframes are sharded r, r+N, ... with a single NCCL all-reduce of the bucket
+(strong scaling: 8 keyframes per step whatever N).  value = 8*steps / time = whole-job frames/s;
+at N = 1 this is exactly the single-GPU fwd+bwd frames/s of the metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`--impl reference` times the UNMODIFIED reference rasterizer compiled from /root/reference
+(oracle/_ref, its own CUDA code path through its own pybind API) on the same workload; the
+reference has no multi-GPU path, so with N > 1 rank 0 alone runs all keyframes.  If the compiled
+reference is absent the CPU oracle port is timed on a bounded sample instead.
+
+Timing rules followed: >= 3 warm-up steps, CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks, nvidia-smi clocks sampled during the timed region.
+Each step's working set (params + per-frame workspaces + gradients, several hundred MB) exceeds
+the 126 MB L2, so no explicit flush is needed between iterations (stated in config.l2).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "mm3dgs-slam_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import gsr_synth as S  # noqa: E402
+
+METRIC = "fwd+bwd frames/s at 1M Gaussians 640x480 (8-keyframe map step)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--P", type=int, default=1_000_000)
+    ap.add_argument("--W", type=int, default=640)
+    ap.add_argument("--H", type=int, default=480)
+    ap.add_argument("--keyframes", type=int, default=8)
+    ap.add_argument("--sh-degree", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# algorithmic bytes per stage: P Gaussians, R tile instances, N pixels, M SH coeffs
+def stage_bytes(P, R, N, M=1):
+    g_in = 44 + 12 * M
+    return {
+        "preprocess_fwd": (g_in + 48) * P,
+        "scan": 8 * P,
+        "duplicate": 12 * R,
+        "sort": 24 * R,
+        "tile_ranges": 8 * R,
+        "render_fwd": 40 * R + 20 * N,
+        "render_bwd": 76 * R + 20 * N,
+        "preprocess_bwd": (g_in + 36 + 48 + g_in) * P,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def build_workload(args, device):
+    gs = S.make_gaussians(args.P, args.W, args.H, seed=0, sh_degree=args.sh_degree)
+    centroid = gs["means3D"][gs["means3D"][:, 2] > 0.1].mean(0).tolist()
+    cams = S.orbit_cameras(args.W, args.H, args.keyframes, centroid, radius=0.5)
+    g = torch.Generator().manual_seed(12345)
+    dL = torch.randn(3, args.H, args.W, generator=g)
+    return gs, cams, dL
+
+
+def settings_list(mod_settings, cams, bg, sh_degree, device):
+    return [mod_settings(image_height=c.H, image_width=c.W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                         scale_modifier=1.0, viewmatrix=c.viewmatrix.to(device), projmatrix=c.projmatrix.to(device),
+                         sh_degree=sh_degree, campos=c.campos.to(device), prefiltered=False, debug=False)
+            for c in cams]
+
+
+def cpu_baseline(args, gs, cam, dL, tile_stride=12):
+    """Oracle port (pure PyTorch, CPU) on a bounded sample of the same workload: full per-Gaussian
+    stages + sort, blend fwd/bwd on every `tile_stride`-th tile, scaled to the full tile count."""
+    from oracle import gs_oracle as O
+    bg = torch.zeros(3)
+    t0 = time.perf_counter()
+    pre = O.preprocess(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix, cam.campos, cam.W, cam.H,
+                       cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], args.sh_degree)
+    binning = O.bin_and_sort(pre, cam.W, cam.H)
+    t1 = time.perf_counter()
+    T = pre["grid"][0] * pre["grid"][1]
+    tiles = list(range(0, T, tile_stride))
+    fwd = O.render_forward(pre, binning, pre["rgb"], bg, cam.W, cam.H, tiles=tiles)
+    rb = O.render_backward(pre, binning, pre["rgb"], bg, fwd, dL, cam.W, cam.H, tiles=tiles)
+    t2 = time.perf_counter()
+    O.preprocess_backward(gs["means3D"], cam.viewmatrix, cam.projmatrix, cam.campos, cam.W, cam.H, cam.tanfovx,
+                          cam.tanfovy, pre, rb, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], args.sh_degree)
+    t3 = time.perf_counter()
+    est = (t1 - t0) + (t2 - t1) * (T / len(tiles)) + (t3 - t2)
+    return {"value": 1.0 / est, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 keyframe of the same scene: all {args.P} Gaussians through preprocess/sort/backward-preprocess, "
+                      f"blend fwd+bwd on {len(tiles)} of {T} tiles (every {tile_stride}th) scaled x{T / len(tiles):.1f}; "
+                      f"{t3 - t0:.1f} s of CPU work, os.cpu_count()={os.cpu_count()}",
+            "est_seconds_per_frame": est}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+    have_cuda = torch.cuda.is_available()
+
+    if args.impl == "reference":
+        from oracle import ref_api
+        if rank != 0:
+            return 0       # the reference has no multi-GPU path: rank 0 alone runs it
+        if not (have_cuda and ref_api.available()):
+            return reference_cpu_port(args)
+    if not have_cuda:
+        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+        return 1
+
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if distributed and args.impl == "b200":
+        dist.init_process_group("nccl", device_id=device)
+
+    gs_cpu, cams, dL_cpu = build_workload(args, device)
+    bg = torch.zeros(3, device=device)
+    dL = dL_cpu.to(device)
+    names = ["means3D", "shs", "opacities", "scales", "rotations"]   # optimizer-group order of the reference
+    params = {k: gs_cpu[k].to(device).requires_grad_(True) for k in names}
+    P, N = args.P, args.W * args.H
+
+    if args.impl == "b200":
+        import diff_gaussian_rasterization as dgr
+        from gsr_mapstep import ShardedMapStep
+        kfs = settings_list(dgr.GaussianRasterizationSettings, cams, bg, args.sh_degree, device)
+
+        def frame_fn(p, rs):
+            m2 = torch.zeros(P, 3, device=device, requires_grad=True)
+            color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"],
+                                                  shs=p["shs"], scales=p["scales"], rotations=p["rotations"])
+            color.backward(dL)
+            return color.detach()
+
+        stepper = ShardedMapStep(params, frame_fn)
+        step = lambda: stepper.step(kfs)  # noqa: E731
+        launch_count = dgr._lib.gsr_launch_count
+        launch_count.restype = ctypes.c_longlong
+    else:
+        from collections import namedtuple
+        RS = namedtuple("RS", "image_height image_width tanfovx tanfovy bg scale_modifier viewmatrix projmatrix "
+                              "sh_degree campos prefiltered debug")
+        kfs = settings_list(RS, cams, bg, args.sh_degree, device)
+
+        def step():
+            for p in params.values():
+                p.grad = None
+            out = []
+            for rs in kfs:
+                m2 = torch.zeros(P, 3, device=device, requires_grad=True)
+                color, _ = ref_api.rasterize(params["means3D"], m2, params["opacities"], rs, shs=params["shs"],
+                                             scales=params["scales"], rotations=params["rotations"])
+                color.backward(dL)
+                out.append(color.detach())
+            return out
+        launch_count = None
+
+    # instance counts for the byte accounting (one untimed forward per keyframe)
+    R_list, vis_list = [], []
+    if args.impl == "b200":
+        with torch.no_grad():
+            for rs in kfs:
+                R, _, radii, _, _, _ = dgr._forward_native(params["means3D"], params["shs"], None, params["opacities"],
+                                                           params["scales"], params["rotations"], None, rs,
+                                                           rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+                R_list.append(R)
+                vis_list.append(int((radii > 0).sum()))
+
+    def barrier():
+        if distributed and args.impl == "b200":
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = launch_count() if launch_count else 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    n1 = launch_count() if launch_count else 0
+    clocks = sampler.stop() if rank == 0 else None
+    if distributed and args.impl == "b200":
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames = args.keyframes * args.steps
+    value = frames / (ms / 1e3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C-main: 1M-Gaussian synthetic scene, 640x480, SH degree 0, 8 orbit keyframes/step"
+                   if (args.P, args.W, args.H, args.keyframes) == (1_000_000, 640, 480, 8) else "custom",
+                   "P": args.P, "W": args.W, "H": args.H, "keyframes_per_step": args.keyframes,
+                   "sh_degree": args.sh_degree, "parallelism": f"keyframe-sharded dp{world}" if args.impl == "b200" else "1 gpu",
+                   "l2": "per-step working set (56 B/G params + 116 B/G grads + per-frame 48 B/G records and "
+                         "24+ B/instance binning, > 400 MB) exceeds the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+    }
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
+                                "sample": "the reference's only implementation is CUDA: compiled unmodified from "
+                                          "/root/reference for sm_100a (oracle/_ref) and run on this GPU, full workload"}
+        line["e2e"] = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        print(json.dumps(line))
+        return 0
+
+    line["gpu_launches"] = int(n1 - n0)
+    line["config"]["R_mean"] = sum(R_list) / max(len(R_list), 1)
+    line["config"]["visible_mean"] = sum(vis_list) / max(len(vis_list), 1)
+
+    # ---- per-stage profile (untimed pass with the library's stage events on) --------------------
+    lib = dgr._lib
+    nst = lib.gsr_profile_num_stages()
+    lib.gsr_profile_stage_name.restype = ctypes.c_char_p
+    lib.gsr_profile_enable(1)
+    torch.cuda.synchronize()
+    ms_arr, cnt_arr = (ctypes.c_float * nst)(), (ctypes.c_int * nst)()
+    lib.gsr_profile_collect(ms_arr, cnt_arr)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    lib.gsr_profile_collect(ms_arr, cnt_arr)
+    lib.gsr_profile_enable(0)
+    my_kfs = len(range(rank, args.keyframes, world))
+    R_mine = [R_list[i] for i in range(rank, args.keyframes, world)]
+    Rm = sum(R_mine) / max(len(R_mine), 1)
+    sb = stage_bytes(P, Rm, N, (args.sh_degree + 1) ** 2)
+    peak, peak_src = measured_peak()
+    stages = {}
+    for i in range(nst):
+        nm = lib.gsr_profile_stage_name(i).decode()
+        if cnt_arr[i] == 0:
+            continue
+        avg = ms_arr[i] / cnt_arr[i]
+        stages[nm] = {"ms": avg, "alg_bytes": sb[nm], "gbs": sb[nm] / (avg * 1e-3) / 1e9}
+    total_ms = sum(s["ms"] for s in stages.values())
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    line["stages"] = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 3), "gbs": round(v["gbs"], 1)}
+                      for k, v in stages.items()}
+    line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                        "alg_bytes_per_launch": stages[dom]["alg_bytes"], "ms_per_launch": stages[dom]["ms"],
+                        "call_alg_bytes": sum(sb.values()), "call_ms_sum_of_stages": total_ms,
+                        "call_frac": sum(sb.values()) / (total_ms * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------
+    if not args.no_e2e:
+        host_in = {k: gs_cpu[k].contiguous().pin_memory() for k in names}
+        host_grad = torch.empty(stepper.bucket.flat.numel(), dtype=torch.float32).pin_memory()
+        host_img = torch.empty(my_kfs, 3, args.H, args.W).pin_memory()
+        h2d = sum(t.numel() * 4 for t in host_in.values())
+        d2h = host_grad.numel() * 4 + host_img.numel() * 4
+
+        def e2e_step():
+            with torch.no_grad():
+                for k in names:
+                    params[k].copy_(host_in[k], non_blocking=True)
+            imgs = step()
+            host_grad.copy_(stepper.bucket.flat, non_blocking=True)
+            for i, im in enumerate(imgs):
+                host_img[i].copy_(im.detach(), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(3, args.steps // 2)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if distributed:
+            t = torch.tensor([ems], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        line["e2e"] = {"value": args.keyframes * n_e2e / (ems / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                       "what": "pinned-host Gaussian parameters copied in, 8-keyframe step through GaussianRasterizer, "
+                               "gradient bucket + rendered images copied back to pinned host memory, every step"}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args, gs_cpu, cams[0], dL_cpu)
+        except Exception as ex:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_cpu_port(args):
+    """Fallback reference arm when the compiled reference is unavailable: the CPU oracle port."""
+    gs, cams, dL = build_workload(args, None)
+    t = time.perf_counter()
+    cb = cpu_baseline(args, gs, cams[0], dL)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": 1, "warmup": 0, "ms_per_step": cb["est_seconds_per_frame"] * 1e3 * args.keyframes,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C-main (CPU oracle port, bounded sample)", "P": args.P, "W": args.W, "H": args.H},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,169 @@
+/*
+ * gsrast_b200.h — C-ABI of the B200-native differentiable 3D-Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of VITA-Group/MM3DGS-SLAM: every entry point
+ * below replaces one native entry of the reference's `diff_gaussian_rasterization._C`
+ * extension (DGR = /root/reference/submodules/diff-gaussian-rasterization):
+ *
+ *   gsr_forward_preprocess + gsr_forward_render
+ *        <- CudaRasterizer::Rasterizer::forward      DGR/cuda_rasterizer/rasterizer.h:35-58,
+ *           bound as _C.rasterize_gaussians           DGR/ext.cpp:16, DGR/rasterize_points.cu:35-115
+ *   gsr_backward
+ *        <- CudaRasterizer::Rasterizer::backward     DGR/cuda_rasterizer/rasterizer.h:60-84,
+ *           bound as _C.rasterize_gaussians_backward  DGR/ext.cpp:17, DGR/rasterize_points.cu:117-196
+ *   gsr_mark_visible
+ *        <- CudaRasterizer::Rasterizer::markVisible  DGR/cuda_rasterizer/rasterizer.h:27-33,
+ *           bound as _C.mark_visible                  DGR/ext.cpp:18, DGR/rasterize_points.cu:198-217
+ *   gsr_*_ws_bytes
+ *        <- required<GeometryState/ImageState/BinningState>()  DGR/cuda_rasterizer/rasterizer_impl.h:67-73
+ *
+ * Plain C: raw device pointers + sizes, no torch / C++ types.  The caller owns every buffer
+ * (including the three opaque scratch workspaces that carry state from forward to backward,
+ * as in the reference); the library keeps no state between calls.  All work is enqueued on
+ * the caller's CUDA stream (the reference uses the legacy default stream; DGR/cuda_rasterizer/
+ * rasterizer_impl.cu:148,289,314).
+ *
+ * Conventions shared with the reference:
+ *   - all arrays are fp32, contiguous, row-major; a NULL pointer means "input absent"
+ *     (the reference's empty-tensor convention, DGR/diff_gaussian_rasterization/__init__.py:197-207);
+ *   - viewmatrix / projmatrix are 16 floats indexed column-major: x' = m[0]x + m[4]y + m[8]z + m[12]
+ *     (DGR/cuda_rasterizer/auxiliary.h:58-77);
+ *   - out_color is planar [3,H,W]; radii is int32 [P]; tiles are 16x16 pixels.
+ *
+ * Every function returns 0 on success or a negative gsr_status; gsr_last_error() gives the message
+ * for the calling thread.  There is no CPU fallback: without a CUDA device every launch fails.
+ */
+#ifndef GSRAST_B200_H_
+#define GSRAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+typedef void* gsr_stream_t; /* cudaStream_t */
+
+enum gsr_status {
+    GSR_OK = 0,
+    GSR_ERR_INVALID = -1, /* bad argument (NULL required pointer, negative size, ...) */
+    GSR_ERR_CUDA = -2,    /* CUDA runtime error; message in gsr_last_error() */
+    GSR_ERR_WORKSPACE = -3 /* workspace too small */
+};
+
+/* Gaussian scene inputs (reference: arguments of Rasterizer::forward, rasterizer.h:39-51). */
+typedef struct gsr_gaussians {
+    int32_t P;                 /* number of Gaussians */
+    int32_t sh_degree;         /* active SH degree D (0..3) */
+    int32_t sh_coeffs;         /* M = coefficients per Gaussian in `shs` (0 if absent) */
+    int32_t _pad;
+    const float* means3D;      /* [P,3] */
+    const float* shs;          /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL (exactly one of shs / colors_precomp) */
+    const float* opacities;    /* [P] */
+    const float* scales;       /* [P,3] or NULL */
+    const float* rotations;    /* [P,4] (r,x,y,z; NOT normalised by the kernel) or NULL */
+    const float* cov3D_precomp; /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
+    float scale_modifier;
+    int32_t _pad2;
+} gsr_gaussians;
+
+/* Camera + raster settings (reference: GaussianRasterizationSettings, __init__.py:157-169). */
+typedef struct gsr_camera {
+    int32_t width, height;
+    float tanfovx, tanfovy;
+    const float* viewmatrix;   /* 16 floats, device */
+    const float* projmatrix;   /* 16 floats, device */
+    const float* campos;       /* 3 floats, device */
+    const float* background;   /* 3 floats, device */
+    int32_t prefiltered;       /* if set, a culled Gaussian traps the kernel (auxiliary.h:154-161) */
+    int32_t debug;             /* if set, synchronise + check after every stage (auxiliary.h:166-173) */
+} gsr_camera;
+
+/* Gradient outputs of gsr_backward.  Shapes as the reference returns them
+ * (DGR/rasterize_points.cu:151-159).  Buffers marked (acc) must be zero-filled by the caller:
+ * the blend backward accumulates into them; the others are fully written by the kernels
+ * (zeros for culled Gaussians), so the caller may leave them uninitialised. */
+typedef struct gsr_grads {
+    float* dL_dmeans2D;   /* [P,3] (acc)  NDC-scaled screen gradient, z always 0 */
+    float* dL_dconic;     /* [P,4] (acc)  internal: d/d(conic) in .x .y .w */
+    float* dL_dopacity;   /* [P]   (acc) */
+    float* dL_dcolors;    /* [P,3] (acc)  d/d(colors_precomp) or internal d/d(rgb) on the SH path */
+    float* dL_dmeans3D;   /* [P,3] */
+    float* dL_dcov3D;     /* [P,6]; may be NULL when cov3D_precomp is absent (not written then) */
+    float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
+    float* dL_dscales;    /* [P,3] or NULL when scales absent */
+    float* dL_drotations; /* [P,4] or NULL when rotations absent */
+    /* Extension over the reference: gradients w.r.t. the camera.  Each may be
+     * NULL (skipped).  (acc): zero-filled by the caller. */
+    float* dL_dviewmatrix; /* [16] (acc) same column-major indexing as the input */
+    float* dL_dprojmatrix; /* [16] (acc) */
+    float* dL_dcampos;     /* [3]  (acc) */
+} gsr_grads;
+
+int gsr_abi_version(void);
+const char* gsr_last_error(void);
+
+/* Workspace sizes in bytes.  geom: per-Gaussian state; img: per-pixel + per-tile state;
+ * binning: sort keys/values for R tile instances (R = num_rendered). */
+size_t gsr_geom_ws_bytes(int32_t P);
+size_t gsr_img_ws_bytes(int32_t width, int32_t height);
+size_t gsr_binning_ws_bytes(int64_t R);
+
+/* Forward, phase 1: per-Gaussian projection / covariance / SH colour / tile counts and their
+ * prefix sum.  Writes radii[P].  If num_rendered is not NULL the call synchronises `stream`
+ * and stores R there (host memory) so the caller can size the binning workspace — this is the
+ * one host sync of the reference (rasterizer_impl.cu:280-281).  The device copy of R stays in
+ * geom_ws for phase 2. */
+int gsr_forward_preprocess(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
+                           int32_t* radii, void* geom_ws, size_t geom_ws_bytes,
+                           void* img_ws, size_t img_ws_bytes, int32_t* num_rendered);
+
+/* Forward, phase 2: tile-instance duplication, (tile|depth) sort, tile ranges, per-tile
+ * front-to-back alpha compositing.  R must be the value phase 1 produced. */
+int gsr_forward_render(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
+                       const int32_t* radii, int64_t R,
+                       void* geom_ws, void* binning_ws, size_t binning_ws_bytes, void* img_ws,
+                       float* out_color);
+
+/* Backward of the whole call. */
+int gsr_backward(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
+                 const int32_t* radii, int64_t R,
+                 const void* geom_ws, const void* binning_ws, const void* img_ws,
+                 const float* dL_dpixels /* [3,H,W] */, const gsr_grads* grads);
+
+/* present[i] = 1 if Gaussian i passes the near-plane test (z_view > 0.1). */
+int gsr_mark_visible(gsr_stream_t stream, int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present);
+
+/* Optional stage profiler (off by default).  When enabled, every stage boundary records a CUDA
+ * event on the caller's stream; gsr_profile_collect() synchronises, sums the elapsed time per stage
+ * since the previous collect into ms[gsr_profile_num_stages()] / counts[...] and resets.
+ * gsr_launch_count(): number of this library's own kernels launched so far in this process. */
+void gsr_profile_enable(int on);
+int gsr_profile_num_stages(void);
+const char* gsr_profile_stage_name(int stage);
+int gsr_profile_collect(float* ms, int* counts);
+long long gsr_launch_count(void);
+
+/* Introspection for tests (sub-buffers of the opaque workspaces; byte offsets from the base). */
+typedef struct gsr_geom_layout {
+    size_t rec;           /* float4[3P]: (px,py,depth,lam_max) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
+    size_t tiles_touched; /* uint32[P] */
+    size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched */
+    size_t scan_temp;     /* scan scratch */
+    size_t total;
+} gsr_geom_layout;
+typedef struct gsr_img_layout { size_t final_T, n_contrib, ranges, total; } gsr_img_layout;
+typedef struct gsr_binning_layout { size_t point_list, keys, point_list_unsorted, keys_unsorted, sort_temp, total; } gsr_binning_layout;
+void gsr_geom_layout_of(int32_t P, gsr_geom_layout* out);
+void gsr_img_layout_of(int32_t width, int32_t height, gsr_img_layout* out);
+void gsr_binning_layout_of(int64_t R, gsr_binning_layout* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSRAST_B200_H_ */

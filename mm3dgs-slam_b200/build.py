@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Build libgsrast_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python mm3dgs-slam_b200/build.py [--force] [--verbose]
+
+Output: mm3dgs-slam_b200/lib/libgsrast_b200.so (git-ignored, travels to the GPU box with gpurun).
+No torch involved: the library is plain CUDA C++ behind the extern "C" API of include/gsrast_b200.h.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+SO = os.path.join(LIBDIR, "libgsrast_b200.so")
+SOURCES = ["preprocess.cu", "binning.cu", "render.cu", "c_api.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# nvcc floating-point defaults on purpose (-fmad=true, IEEE div/sqrt, no fast-math): the integer
+# outputs (radii, tile rectangles, sort keys) must match the reference build bit for bit.
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+          "--expt-relaxed-constexpr", "-DGSR_BUILD"]
+
+
+def _deps():
+    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    d.append(os.path.join(HERE, "..", "include", "gsrast_b200.h"))
+    return d
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def _run(cmd, verbose):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 or verbose:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed")
+
+
+def build(force=False, verbose=False, ptxas_info=False):
+    if not force and not needs_build():
+        return SO
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if ptxas_info else []
+    jobs, objs = [], []
+    for s in SOURCES:
+        o = os.path.join(objdir, s + ".o")
+        objs.append(o)
+        jobs.append([NVCC, "-c", os.path.join(CSRC, s), "-o", o] + ARCH + CFLAGS + extra)
+    with ThreadPoolExecutor(len(jobs)) as ex:
+        list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))
+    _run([NVCC, "-shared", "-o", SO] + objs + ARCH + ["-cudart", "shared", "-Xcompiler", "-fPIC"], verbose)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_info="--ptxas" in sys.argv))

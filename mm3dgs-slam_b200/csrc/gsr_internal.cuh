@@ -1,0 +1,93 @@
+// gsr_internal.cuh — workspace layouts and launcher prototypes shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/gsrast_b200.h"
+
+namespace gsr {
+
+constexpr int kTile = 16;
+constexpr size_t kAlign = 256;
+
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+// ---- per-Gaussian state ---------------------------------------------------------------------
+// One 48-byte record per Gaussian so that the blend kernels gather a single contiguous chunk:
+//   rec[3i+0] = (px, py, depth, lam_max)        pixel mean, view depth, larger cov2D eigenvalue
+//   rec[3i+1] = (conic.x, conic.y, conic.z, opacity)
+//   rec[3i+2] = (r, g, b, bits)                 bits: SH clamp flags (bit ch set => channel clamped)
+// The reference keeps these in separate arrays (GeometryState, CR/rasterizer_impl.h:29-44) and
+// additionally stores cov3D (24 B) which the backward here recomputes from scale/rotation.
+struct GeomWS {
+    float4* rec;
+    uint32_t* tiles_touched;
+    uint32_t* point_offsets;
+    char* scan_temp;
+    size_t scan_temp_bytes;
+    size_t total;
+};
+struct ImgWS {
+    float* final_T;
+    uint32_t* n_contrib;
+    uint2* ranges;
+    size_t total;
+};
+struct BinWS {
+    uint32_t* point_list;
+    uint64_t* keys;
+    uint32_t* point_list_unsorted;
+    uint64_t* keys_unsorted;
+    char* sort_temp;
+    size_t sort_temp_bytes;
+    size_t total;
+};
+
+GeomWS geom_ws_carve(char* base, int P);
+ImgWS img_ws_carve(char* base, int W, int H);
+BinWS bin_ws_carve(char* base, int64_t R);
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(int64_t R);
+
+// ---- launchers (each enqueues on `s`) ---------------------------------------------------------
+struct PreArgs {
+    int P, D, M, W, H, gx, gy, prefiltered;
+    const float *means, *scales, *rots, *opac, *shs, *colors, *cov3D_pre, *view, *proj, *campos;
+    float scale_mod, tanfovx, tanfovy, focal_x, focal_y;
+    int* radii;
+    float4* rec;
+    uint32_t* tiles;
+};
+void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s);
+void launch_mark_visible(int P, const float* means, const float* view, const float* proj, uint8_t* present,
+                         cudaStream_t s);
+
+void launch_scan(const uint32_t* in, uint32_t* out, int P, char* temp, size_t temp_bytes, cudaStream_t s);
+void launch_duplicate(int P, const float4* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
+                      uint32_t* vals, int gx, int gy, cudaStream_t s);
+void launch_sort(BinWS& b, int64_t R, int end_bit, cudaStream_t s);
+void launch_tile_ranges(int64_t R, const uint64_t* keys, uint2* ranges, int tiles, cudaStream_t s);
+
+void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+                       const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
+                       cudaStream_t s);
+void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+                       const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
+                       const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
+                       float* dL_dopacity, float* dL_dcolors /*[P,3]*/, cudaStream_t s);
+
+struct PreBwdArgs {
+    int P, D, M, W, H;
+    const float *means, *scales, *rots, *shs, *cov3D_pre, *view, *proj, *campos;
+    float scale_mod, tanfovx, tanfovy, focal_x, focal_y;
+    const int* radii;
+    const float4* rec;
+    const float* dL_dmean2D;  // [P,3]
+    const float* dL_dconic;   // [P,4]
+    const float* dL_dcolors;  // [P,3]
+    float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots;
+    float *dL_dview, *dL_dproj, *dL_dcampos;
+};
+void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
+
+}  // namespace gsr

@@ -1,0 +1,328 @@
+// render.cu — per-tile alpha compositing, forward and backward.
+//
+// Replaces renderCUDA forward (CR/forward.cu:261-374) and backward (CR/backward.cu:399-557).
+// Per-pixel semantics are identical (same skip rules, same sequential blend order, same
+// `contributor` bookkeeping); what changes is how the work is organised for sm_100a:
+//
+//  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4-pixel sub-tile so that the set of
+//    splats touching a warp is compact;
+//  * the tile's splat list is staged 256 records at a time into shared memory — one 48-byte
+//    record per splat (position, conic, opacity, colour) instead of the reference's three global
+//    arrays plus a per-(pixel,splat) colour gather from global memory;
+//  * each warp first culls the staged batch against its sub-tile with a conservative circle test
+//    (one splat per lane, __ballot_sync), then walks only the surviving bits — splats that cannot
+//    reach alpha >= 1/255 anywhere in the sub-tile are never evaluated.  The test is conservative,
+//    so exactly the same (pixel, splat) pairs contribute as in the reference;
+//  * early termination is per warp (__all_sync on the running transmittance), the CTA leaves when
+//    all 8 warps are done;
+//  * backward: the traversal starts at the CTA-wide last contributor instead of the end of the
+//    list, the 9 per-splat gradient terms are reduced over the warp with shuffles, combined over
+//    the 8 warps in shared memory, and leave the CTA as ONE red.global per (tile, splat, term)
+//    instead of one atomicAdd per (pixel, splat, term).
+#include "gsr_internal.cuh"
+
+namespace gsr {
+
+constexpr int kBatch = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct TileGeom {
+    int px, py;       // this lane's pixel
+    float sx0, sx1;   // sub-tile pixel-centre extent
+    float sy0, sy1;
+    bool inside;
+};
+
+__device__ __forceinline__ TileGeom tile_geom(int tile, int gx, int W, int H)
+{
+    TileGeom g;
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ox = tx * kTile + (warp & 1) * 8, oy = ty * kTile + (warp >> 1) * 4;
+    g.px = ox + (lane & 7);
+    g.py = oy + (lane >> 3);
+    g.sx0 = (float)ox;
+    g.sx1 = (float)(ox + 7);
+    g.sy0 = (float)oy;
+    g.sy1 = (float)(oy + 3);
+    g.inside = g.px < W && g.py < H;
+    return g;
+}
+
+// Conservative test: can a splat centred at (x,y) with cull radius^2 rc2 touch the sub-tile?
+// Written as !(d2 > rc2) so that a NaN radius never culls.
+__device__ __forceinline__ bool subtile_hit(const TileGeom& g, float x, float y, float rc2)
+{
+    const float dx = fmaxf(0.f, fmaxf(g.sx0 - x, x - g.sx1));
+    const float dy = fmaxf(0.f, fmaxf(g.sy0 - y, y - g.sy1));
+    return !(dx * dx + dy * dy > rc2);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Forward
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                    const uint32_t* __restrict__ point_list,
+                                                    const float4* __restrict__ rec, const float* __restrict__ bg,
+                                                    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                                                    float* __restrict__ out_color)
+{
+    __shared__ float4 s_r0[kBatch];  // px, py, depth, cull r^2
+    __shared__ float4 s_r1[kBatch];  // conic xyz, opacity
+    __shared__ float4 s_r2[kBatch];  // rgb, bits
+
+    const int tile = blockIdx.x;
+    const TileGeom g = tile_geom(tile, gx, W, H);
+    const int lane = threadIdx.x & 31;
+    const float pixx = (float)g.px, pixy = (float)g.py;
+    const uint2 range = ranges[tile];
+    const int n = (int)(range.y - range.x);
+
+    float T = 1.0f;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t last_contributor = 0;
+    bool done = !g.inside;
+    bool warp_done = __all_sync(kFull, done);
+
+    for (int base = 0; base < n; base += kBatch) {
+        if (__syncthreads_and(warp_done)) break;
+        const int i = base + (int)threadIdx.x;
+        if (i < n) {
+            const uint32_t id = point_list[range.x + i];
+            const float4* r = rec + (size_t)id * 3;
+            s_r0[threadIdx.x] = __ldg(r);
+            s_r1[threadIdx.x] = __ldg(r + 1);
+            s_r2[threadIdx.x] = __ldg(r + 2);
+        }
+        __syncthreads();
+        if (warp_done) continue;
+        const int cnt = min(kBatch, n - base);
+        for (int k = 0; k < cnt; k += 32) {
+            bool hit = false;
+            if (k + lane < cnt) {
+                const float4 a = s_r0[k + lane];
+                hit = subtile_hit(g, a.x, a.y, a.w);
+            }
+            unsigned m = __ballot_sync(kFull, hit);
+            while (m) {
+                const int j = k + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 a = s_r0[j];
+                const float4 co = s_r1[j];
+                const float dx = a.x - pixx, dy = a.y - pixy;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                const float alpha = fminf(0.99f, co.w * expf(power));
+                const float test_T = T * (1 - alpha);
+                const bool live = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                if (live) {
+                    if (test_T < 0.0001f) {
+                        done = true;
+                    } else {
+                        const float4 c = s_r2[j];
+                        const float w = alpha * T;
+                        C0 += c.x * w;
+                        C1 += c.y * w;
+                        C2 += c.z * w;
+                        T = test_T;
+                        last_contributor = (uint32_t)(base + j + 1);
+                    }
+                }
+            }
+            if (__all_sync(kFull, done)) {
+                warp_done = true;
+                break;
+            }
+        }
+    }
+    if (g.inside) {
+        const int pix = g.py * W + g.px;
+        final_T[pix] = T;
+        n_contrib[pix] = last_contributor;
+        const size_t HW = (size_t)H * W;
+        out_color[pix] = C0 + T * bg[0];
+        out_color[HW + pix] = C1 + T * bg[1];
+        out_color[2 * HW + pix] = C2 + T * bg[2];
+    }
+}
+
+void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+                       const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
+                       cudaStream_t s)
+{
+    k_render_fwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, out_color);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Backward
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                    const uint32_t* __restrict__ point_list,
+                                                    const float4* __restrict__ rec, const float* __restrict__ bg,
+                                                    const float* __restrict__ final_T,
+                                                    const uint32_t* __restrict__ n_contrib,
+                                                    const float* __restrict__ dL_dpix, float* __restrict__ dL_dmean2D,
+                                                    float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+                                                    float* __restrict__ dL_dcolors)
+{
+    __shared__ float4 s_r0[kBatch];
+    __shared__ float4 s_r1[kBatch];
+    __shared__ float4 s_r2[kBatch];
+    __shared__ uint32_t s_id[kBatch];
+    __shared__ float s_acc[9][kBatch];   // per staged splat: m2x m2y cx cy cw op cr cg cb
+    __shared__ uint32_t s_touched[kBatch / 32];
+    __shared__ uint32_t s_max;
+
+    const int tile = blockIdx.x;
+    const TileGeom g = tile_geom(tile, gx, W, H);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float pixx = (float)g.px, pixy = (float)g.py;
+    const uint2 range = ranges[tile];
+    const int pix = g.py * W + g.px;
+    const size_t HW = (size_t)H * W;
+
+    const float T_final = g.inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    const uint32_t last_contributor = g.inside ? n_contrib[pix] : 0u;
+    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
+    if (g.inside) {
+        dLp0 = dL_dpix[pix];
+        dLp1 = dL_dpix[HW + pix];
+        dLp2 = dL_dpix[2 * HW + pix];
+    }
+    const float bg_dot_dpixel = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;  // last colour / alpha
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int bmax = (int)s_max;   // CTA-wide last contributor: nothing behind it matters
+
+    for (int hi = bmax; hi > 0; hi -= kBatch) {
+        // staged slot t holds list position hi-1-t (back to front)
+        const int cnt = min(kBatch, hi);
+        __syncthreads();
+        {
+            const int t = threadIdx.x;
+            if (t < cnt) {
+                const uint32_t id = point_list[range.x + (uint32_t)(hi - 1 - t)];
+                const float4* r = rec + (size_t)id * 3;
+                s_id[t] = id;
+                s_r0[t] = __ldg(r);
+                s_r1[t] = __ldg(r + 1);
+                s_r2[t] = __ldg(r + 2);
+            }
+#pragma unroll
+            for (int k = 0; k < 9; k++) s_acc[k][t] = 0.f;
+            if (t < kBatch / 32) s_touched[t] = 0u;
+        }
+        __syncthreads();
+        // first slot this warp cares about: position < wmax  <=>  t > hi-1-wmax
+        int t0 = hi - (int)wmax;
+        if (t0 < 0) t0 = 0;
+        for (int k = (t0 & ~31); k < cnt; k += 32) {
+            bool hit = false;
+            const int tt = k + lane;
+            if (tt < cnt && tt >= t0) {
+                const float4 a = s_r0[tt];
+                hit = subtile_hit(g, a.x, a.y, a.w);
+            }
+            unsigned m = __ballot_sync(kFull, hit);
+            unsigned touched = 0u;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                const int j = k + b;
+                m &= m - 1;
+                const uint32_t pos = (uint32_t)(hi - 1 - j);   // 0-based list position
+                const float4 a = s_r0[j];
+                const float4 co = s_r1[j];
+                const float dx = a.x - pixx, dy = a.y - pixy;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, co.w * G);
+                const bool live = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
+                if (live) {
+                    const float4 c = s_r2[j];
+                    T = T / (1.f - alpha);
+                    const float dchannel_dcolor = alpha * T;
+                    float dL_dalpha = 0.0f;
+                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                    lc0 = c.x;
+                    dL_dalpha += (c.x - acc0) * dLp0;
+                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                    lc1 = c.y;
+                    dL_dalpha += (c.y - acc1) * dLp1;
+                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                    lc2 = c.z;
+                    dL_dalpha += (c.z - acc2) * dLp2;
+                    v6 = dchannel_dcolor * dLp0;
+                    v7 = dchannel_dcolor * dLp1;
+                    v8 = dchannel_dcolor * dLp2;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                    const float dL_dG = co.w * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                    const float dG_ddely = -gdy * co.z - gdx * co.y;
+                    v0 = dL_dG * dG_ddelx * ddelx_dx;
+                    v1 = dL_dG * dG_ddely * ddely_dy;
+                    v2 = -0.5f * gdx * dx * dL_dG;
+                    v3 = -0.5f * gdx * dy * dL_dG;
+                    v4 = -0.5f * gdy * dy * dL_dG;
+                    v5 = G * dL_dalpha;
+                }
+                if (__any_sync(kFull, live)) {
+                    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+                    v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
+                    v6 = warp_sum(v6); v7 = warp_sum(v7); v8 = warp_sum(v8);
+                    if (lane == 0) {
+                        atomicAdd(&s_acc[0][j], v0); atomicAdd(&s_acc[1][j], v1); atomicAdd(&s_acc[2][j], v2);
+                        atomicAdd(&s_acc[3][j], v3); atomicAdd(&s_acc[4][j], v4); atomicAdd(&s_acc[5][j], v5);
+                        atomicAdd(&s_acc[6][j], v6); atomicAdd(&s_acc[7][j], v7); atomicAdd(&s_acc[8][j], v8);
+                    }
+                    touched |= 1u << b;
+                }
+            }
+            if (lane == 0 && touched) atomicOr(&s_touched[k >> 5], touched);
+        }
+        __syncthreads();
+        {
+            const int t = threadIdx.x;
+            if (t < cnt && ((s_touched[t >> 5] >> (t & 31)) & 1u)) {
+                const size_t id = s_id[t];
+                atomicAdd(dL_dmean2D + id * 3 + 0, s_acc[0][t]);
+                atomicAdd(dL_dmean2D + id * 3 + 1, s_acc[1][t]);
+                atomicAdd(dL_dconic + id * 4 + 0, s_acc[2][t]);
+                atomicAdd(dL_dconic + id * 4 + 1, s_acc[3][t]);
+                atomicAdd(dL_dconic + id * 4 + 3, s_acc[4][t]);
+                atomicAdd(dL_dopacity + id, s_acc[5][t]);
+                atomicAdd(dL_dcolors + id * 3 + 0, s_acc[6][t]);
+                atomicAdd(dL_dcolors + id * 3 + 1, s_acc[7][t]);
+                atomicAdd(dL_dcolors + id * 3 + 2, s_acc[8][t]);
+            }
+        }
+    }
+}
+
+void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+                       const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
+                       const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                       float* dL_dcolors, cudaStream_t s)
+{
+    k_render_bwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix,
+                                         dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
+}
+
+}  // namespace gsr

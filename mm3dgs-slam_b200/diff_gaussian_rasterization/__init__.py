@@ -1,0 +1,329 @@
+"""Drop-in replacement for the reference's `diff_gaussian_rasterization` package, backed by the
+B200-native C-ABI library `libgsrast_b200.so` (include/gsrast_b200.h).
+
+Mirrors the public surface of DGR/diff_gaussian_rasterization/__init__.py
+(DGR = /root/reference/submodules/diff-gaussian-rasterization):
+
+    GaussianRasterizationSettings   (__init__.py:157-169)  same fields, same order
+    GaussianRasterizer              (__init__.py:171-220)  .forward(...) -> (color[3,H,W], radii[P]); .markVisible
+    rasterize_gaussians             (__init__.py:21-42)    same positional signature
+
+so `slam/renderer.py` (R/slam/renderer.py:15-18,140,196-214) imports and calls it unchanged.
+Same error behaviour: plain `Exception` for the SH/colour and scale/covariance exclusivity checks
+(__init__.py:191-195), `RuntimeError` for a mis-shaped means3D (DGR/rasterize_points.cu:57-59),
+argument snapshot on failure when `debug` is set (__init__.py:83-90,132-139).
+
+Differences, all additive:
+  * work is enqueued on torch's CURRENT stream (the reference uses the legacy default stream);
+  * `viewmatrix`, `projmatrix` and `campos` are differentiable: if the tensors inside
+    `raster_settings` require grad they receive gradients;
+  * there is no CPU path and no fallback: importing this module without the built CUDA library
+    raises ImportError, and calling it with non-CUDA tensors raises RuntimeError.
+
+Host code here is plumbing only (allocation + ctypes marshalling); all compute is in the library.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+
+# ------------------------------------------------------------------------------------------------
+# Library loading
+# ------------------------------------------------------------------------------------------------
+_LIB_PATH = os.environ.get(
+    "GSRAST_B200_LIB",
+    os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "lib", "libgsrast_b200.so"),
+)
+
+
+class _Gaussians(ctypes.Structure):
+    _fields_ = [
+        ("P", ctypes.c_int32), ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32), ("_pad", ctypes.c_int32),
+        ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p),
+        ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
+        ("cov3D_precomp", ctypes.c_void_p), ("scale_modifier", ctypes.c_float), ("_pad2", ctypes.c_int32),
+    ]
+
+
+class _Camera(ctypes.Structure):
+    _fields_ = [
+        ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("tanfovx", ctypes.c_float), ("tanfovy", ctypes.c_float),
+        ("viewmatrix", ctypes.c_void_p), ("projmatrix", ctypes.c_void_p), ("campos", ctypes.c_void_p),
+        ("background", ctypes.c_void_p), ("prefiltered", ctypes.c_int32), ("debug", ctypes.c_int32),
+    ]
+
+
+class _Grads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "dL_dmeans2D", "dL_dconic", "dL_dopacity", "dL_dcolors", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+        "dL_dscales", "dL_drotations", "dL_dviewmatrix", "dL_dprojmatrix", "dL_dcampos")]
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"diff_gaussian_rasterization (B200): CUDA library not found at {_LIB_PATH}. "
+            "Build it with `python mm3dgs-slam_b200/build.py` (or __graft_entry__.build()). "
+            "There is no CPU fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+    lib.gsr_abi_version.restype = ctypes.c_int
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    lib.gsr_geom_ws_bytes.restype = sz
+    lib.gsr_geom_ws_bytes.argtypes = [i32]
+    lib.gsr_img_ws_bytes.restype = sz
+    lib.gsr_img_ws_bytes.argtypes = [i32, i32]
+    lib.gsr_binning_ws_bytes.restype = sz
+    lib.gsr_binning_ws_bytes.argtypes = [i64]
+    lib.gsr_forward_preprocess.restype = ctypes.c_int
+    lib.gsr_forward_preprocess.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, vp, sz, vp, sz,
+                                           ctypes.POINTER(i32)]
+    lib.gsr_forward_render.restype = ctypes.c_int
+    lib.gsr_forward_render.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, i64, vp, vp, sz, vp, vp]
+    lib.gsr_backward.restype = ctypes.c_int
+    lib.gsr_backward.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, i64, vp, vp, vp, vp,
+                                 ctypes.POINTER(_Grads)]
+    lib.gsr_mark_visible.restype = ctypes.c_int
+    lib.gsr_mark_visible.argtypes = [vp, i32, vp, vp, vp, vp]
+    if lib.gsr_abi_version() != 1:
+        raise ImportError("libgsrast_b200.so ABI version mismatch")
+    return lib
+
+
+_lib = _load()
+
+
+def _check(rc):
+    if rc != 0:
+        msg = _lib.gsr_last_error()
+        raise RuntimeError("gsrast_b200: " + (msg.decode() if msg else f"error {rc}"))
+
+
+def _ptr(t):
+    """Device pointer of a tensor, or NULL for the reference's 'empty tensor = absent' convention."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _prep(t, device):
+    """fp32, contiguous, on `device` (no copy when already so)."""
+    if t is None or t.numel() == 0:
+        return t
+    if t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+def _snapshot(args, path):
+    torch.save(tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args), path)
+
+
+# ------------------------------------------------------------------------------------------------
+# Native calls
+# ------------------------------------------------------------------------------------------------
+def _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg):
+    P = means3D.shape[0]
+    M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
+    g = _Gaussians(P, int(rs.sh_degree), M, 0, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
+                   _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp), float(rs.scale_modifier), 0)
+    c = _Camera(int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy), _ptr(view), _ptr(proj),
+                _ptr(campos), _ptr(bg), int(bool(rs.prefiltered)), int(bool(rs.debug)))
+    return g, c
+
+
+def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg):
+    dev = means3D.device
+    P = means3D.shape[0]
+    H, W = int(rs.image_height), int(rs.image_width)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    u8 = dict(dtype=torch.uint8, device=dev)
+    color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    if P == 0:
+        color.zero_()
+        e = torch.empty(0, **u8)
+        return 0, color, radii, e, e, e
+    geom = torch.empty(_lib.gsr_geom_ws_bytes(P), **u8)
+    img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
+    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg)
+    R = ctypes.c_int32(0)
+    _check(_lib.gsr_forward_preprocess(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), geom.data_ptr(),
+                                       geom.numel(), img.data_ptr(), img.numel(), ctypes.byref(R)))
+    R = int(R.value)
+    binning = torch.empty(_lib.gsr_binning_ws_bytes(R), **u8)
+    _check(_lib.gsr_forward_render(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, geom.data_ptr(),
+                                   binning.data_ptr(), binning.numel(), img.data_ptr(), color.data_ptr()))
+    return R, color, radii, geom, binning, img
+
+
+def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view,
+                     proj, campos, bg, radii, R, geom, binning, img, want_cam):
+    dev = means3D.device
+    P = means3D.shape[0]
+    M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
+    f32 = dict(dtype=torch.float32, device=dev)
+    # accumulated-into buffers share one zero fill: [means2D 3 | conic 4 | opacity 1 | colors 3] per Gaussian
+    acc = torch.zeros(P * 11, **f32)
+    g_means2D = acc[: 3 * P].view(P, 3)
+    g_conic = acc[3 * P: 7 * P].view(P, 4)
+    g_opacity = acc[7 * P: 8 * P].view(P, 1)
+    g_colors = acc[8 * P: 11 * P].view(P, 3)
+    g_means3D = torch.empty((P, 3), **f32)
+    has_sr = scales is not None and scales.numel() != 0
+    has_cov = cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0
+    g_cov3D = torch.empty((P, 6), **f32) if has_cov else None
+    g_sh = torch.empty((P, M, 3), **f32) if M > 0 else None
+    g_scales = torch.empty((P, 3), **f32) if has_sr else None
+    g_rots = torch.empty((P, 4), **f32) if has_sr else None
+    g_cam = torch.zeros(35, **f32) if want_cam else None
+    if P == 0:
+        return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg)
+    gr = _Grads(g_means2D.data_ptr(), g_conic.data_ptr(), g_opacity.data_ptr(), g_colors.data_ptr(),
+                g_means3D.data_ptr(), _ptr(g_cov3D), _ptr(g_sh), _ptr(g_scales), _ptr(g_rots),
+                g_cam.data_ptr() if want_cam else None,
+                g_cam.data_ptr() + 64 if want_cam else None,
+                g_cam.data_ptr() + 128 if want_cam else None)
+    _check(_lib.gsr_backward(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, _ptr(geom), _ptr(binning),
+                             _ptr(img), grad_color.data_ptr(), ctypes.byref(gr)))
+    return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam
+
+
+# ------------------------------------------------------------------------------------------------
+# Public API (same names and argument meaning as the reference)
+# ------------------------------------------------------------------------------------------------
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    rs = raster_settings
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings, viewmatrix, projmatrix, campos):
+        rs = raster_settings
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise RuntimeError("gsrast_b200: tensors must live on a CUDA device (there is no CPU path)")
+        dev = means3D.device
+        with torch.cuda.device(dev):
+            t = [_prep(x, dev) for x in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                         viewmatrix, projmatrix, campos, rs.bg)]
+            means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_ = t
+            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_)
+            if rs.debug:
+                try:
+                    out = _forward_native(*args)
+                except Exception:
+                    _snapshot(args, "snapshot_fw.dump")
+                    print("\ngsrast_b200: forward failed; arguments written to snapshot_fw.dump")
+                    raise
+            else:
+                out = _forward_native(*args)
+        num_rendered, color, radii, geom, binning, img = out
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, radii,
+                              geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        rs = ctx.raster_settings
+        (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, view, proj, campos, bg, radii,
+         geom, binning, img) = ctx.saved_tensors
+        dev = means3D.device
+        want_cam = any(ctx.needs_input_grad[9:12])
+        with torch.cuda.device(dev):
+            grad = _prep(grad_out_color, dev)
+            args = (grad, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj,
+                    campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam)
+            if rs.debug:
+                try:
+                    res = _backward_native(*args)
+                except Exception:
+                    _snapshot(args, "snapshot_bw.dump")
+                    print("\ngsrast_b200: backward failed; arguments written to snapshot_bw.dump")
+                    raise
+            else:
+                res = _backward_native(*args)
+        g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam = res
+        has_colors = colors_precomp is not None and colors_precomp.numel() != 0
+        g_view = g_proj = g_campos = None
+        if g_cam is not None:
+            g_view = g_cam[0:16].view_as(view) if ctx.needs_input_grad[9] else None
+            g_proj = g_cam[16:32].view_as(proj) if ctx.needs_input_grad[10] else None
+            g_campos = g_cam[32:35].view_as(campos) if ctx.needs_input_grad[11] else None
+        if opacities.dim() == 1:
+            g_opacity = g_opacity.view(-1)
+        return (g_means3D, g_means2D, g_sh, g_colors if has_colors else None, g_opacity, g_scales, g_rots, g_cov3D,
+                None, g_view, g_proj, g_campos)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """bool[P]: Gaussians that pass the near-plane frustum test for this camera."""
+        rs = self.raster_settings
+        with torch.no_grad():
+            if not positions.is_cuda:
+                raise RuntimeError("gsrast_b200: tensors must live on a CUDA device (there is no CPU path)")
+            dev = positions.device
+            pos = _prep(positions, dev)
+            P = pos.shape[0]
+            present = torch.zeros((P,), dtype=torch.uint8, device=dev)
+            if P:
+                with torch.cuda.device(dev):
+                    view, proj = _prep(rs.viewmatrix, dev), _prep(rs.projmatrix, dev)
+                    _check(_lib.gsr_mark_visible(torch.cuda.current_stream(dev).cuda_stream, P, pos.data_ptr(),
+                                                 view.data_ptr(), proj.data_ptr(), present.data_ptr()))
+            return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.Tensor([])
+        return rasterize_gaussians(
+            means3D, means2D,
+            empty if shs is None else shs,
+            empty if colors_precomp is None else colors_precomp,
+            opacities,
+            empty if scales is None else scales,
+            empty if rotations is None else rotations,
+            empty if cov3D_precomp is None else cov3D_precomp,
+            rs)

@@ -1,0 +1,83 @@
+"""Keyframe-sharded mapping step: one process per GPU, replicated Gaussian
+parameters, each rank renders + back-propagates its share of the K keyframes of the covisibility
+window, and ONE all-reduce(SUM) over a flat fp32 gradient bucket combines them.
+
+The reference optimises one random keyframe per Adam step and has no distributed code
+(R/slam/mapper.py:797-828,938-939); the single-GPU ground truth of this construct is plain
+gradient accumulation over the same K keyframes followed by one optimizer step, which is exactly
+what `ShardedMapStep` computes at world_size == 1.
+
+Gradients land directly in the bucket: every parameter's `.grad` is a view into one contiguous
+tensor (14 floats = 56 B per Gaussian at SH degree 0, in the order of the reference's optimizer
+groups, R/slam/gaussian_model.py:151-187), autograd accumulates in place, and the collective runs
+on that tensor without a gather/flatten copy.  Rank r takes keyframes r, r+G, r+2G, ...; ranks with
+no keyframe still join the all-reduce with zeros.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucket:
+    """One flat fp32 tensor holding the gradients of all parameters, exposed as per-parameter views."""
+
+    def __init__(self, params: Dict[str, torch.Tensor]):
+        self.names = list(params.keys())
+        self.params = params
+        n = sum(p.numel() for p in params.values())
+        first = next(iter(params.values()))
+        self.flat = torch.zeros(n, dtype=torch.float32, device=first.device)
+        self.views: Dict[str, torch.Tensor] = {}
+        off = 0
+        for k, p in params.items():
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise ValueError(f"parameter {k} must be contiguous fp32")
+            self.views[k] = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+        self.attach()
+
+    def attach(self):
+        """(Re)bind every parameter's .grad to its bucket view so autograd accumulates in place."""
+        for k, p in self.params.items():
+            p.grad = self.views[k]
+
+    def zero_(self):
+        self.flat.zero_()
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+
+def shard_keyframes(num_keyframes: int, rank: int, world: int) -> List[int]:
+    """Indices of the keyframes rank `rank` owns: r, r+G, r+2G, ..."""
+    return list(range(rank, num_keyframes, world))
+
+
+class ShardedMapStep:
+    """frame_fn(params, keyframe) must run forward + backward for one keyframe, accumulating into the
+    parameters' .grad (it may return a detached scalar loss)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], frame_fn: Callable, group: Optional[dist.ProcessGroup] = None):
+        self.params = params
+        self.bucket = GradBucket(params)
+        self.frame_fn = frame_fn
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+
+    def my_keyframes(self, keyframes: Sequence):
+        return [keyframes[i] for i in shard_keyframes(len(keyframes), self.rank, self.world)]
+
+    def step(self, keyframes: Sequence):
+        """Sum of per-keyframe gradients in self.bucket.flat on every rank. Returns the local losses."""
+        self.bucket.zero_()
+        self.bucket.attach()
+        losses = [self.frame_fn(self.params, kf) for kf in self.my_keyframes(keyframes)]
+        if self.world > 1:
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+        return losses

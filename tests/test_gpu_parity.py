@@ -1,0 +1,261 @@
+"""GPU parity tests: the B200 library (through its C-ABI, via the drop-in Python package) against
+(1) the CPU oracle (oracle/gs_oracle.py) and (2) the compiled reference (oracle/_ref) on identical
+seeded inputs.  Tolerances: integer / index outputs bit-exact; images and gradients within 1e-4
+relative (BASELINE.json north_star)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dgr(built_lib):
+    import diff_gaussian_rasterization as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_api
+    if not ref_api.available():
+        pytest.skip("compiled reference (oracle/_ref) not present")
+    ref_api.load()
+    return ref_api
+
+
+def _run(mod_rasterize, gs, rs, dL, mode):
+    """One forward+backward through an autograd rasterizer; returns image, radii and grads."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in gs.items()}
+    P = gs["means3D"].shape[0]
+    means2D = torch.zeros(P, 3, device=gs["means3D"].device, requires_grad=True)
+    kw = dict(scales=leaves["scales"], rotations=leaves["rotations"])
+    if mode == "sh":
+        kw["shs"] = leaves["shs"]
+    elif mode == "colors":
+        leaves["colors"] = (gs["shs"][:, 0] * 0.28209479177387814 + 0.5).clamp(min=0).clone().requires_grad_(True)
+        kw["colors_precomp"] = leaves["colors"]
+    color, radii = mod_rasterize(leaves["means3D"], means2D, leaves["opacities"], rs, **kw)
+    (color * dL).sum().backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    grads["means2D"] = means2D.grad
+    return color.detach(), radii.detach(), grads
+
+
+def _ours(dgr):
+    def f(means3D, means2D, opacities, rs, **kw):
+        return dgr.GaussianRasterizer(rs)(means3D=means3D, means2D=means2D, opacities=opacities, **kw)
+    return f
+
+
+def _theirs(ref):
+    def f(means3D, means2D, opacities, rs, **kw):
+        return ref.rasterize(means3D, means2D, opacities, rs, **kw)
+    return f
+
+
+CASES = [
+    # P, W, H, sh_degree, mode, seed
+    (300, 64, 48, 0, "sh", 1),
+    (1000, 64, 48, 3, "sh", 2),
+    (2000, 128, 96, 1, "sh", 3),
+    (5000, 200, 120, 0, "colors", 4),     # ragged: neither dimension a multiple of 16
+    (20000, 320, 240, 0, "sh", 5),
+    (100000, 320, 240, 0, "sh", 0),       # BASELINE config 2
+]
+
+
+@pytest.mark.parametrize("P,W,H,deg,mode,seed", CASES)
+def test_vs_reference(dgr, ref, P, W, H, deg, mode, seed):
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    gs, cam, dL, bg = scene_on(dev, P, W, H, seed, deg)
+    bg = torch.tensor([0.1, 0.3, 0.6], device=dev) if seed % 2 else bg
+    rs = settings_for(dgr, cam, bg, deg, dev)
+    c1, r1, g1 = _run(_ours(dgr), gs, rs, dL, mode)
+    c2, r2, g2 = _run(_theirs(ref), gs, rs, dL, mode)
+    assert torch.equal(r1, r2), f"radii differ in {(r1 != r2).sum().item()} of {P}"
+    assert rel_err(c1, c2) < TOL
+    for k in g2:
+        assert torch.isfinite(g1[k]).all(), k
+        assert rel_err(g1[k], g2[k]) < TOL, (k, rel_err(g1[k], g2[k]))
+
+
+@pytest.mark.parametrize("P,W,H,deg,seed", [(3000, 128, 96, 0, 7), (100000, 320, 240, 0, 0), (50000, 640, 480, 2, 9)])
+def test_intermediate_state_bit_exact(dgr, ref, P, W, H, deg, seed):
+    """tiles_touched, sort keys, sorted Gaussian lists, tile ranges and n_contrib match bit for bit;
+    per-Gaussian 2-D quantities match to float rounding."""
+    from tests import ws_decode
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    gs, cam, dL, bg = scene_on(dev, P, W, H, seed, deg)
+    rs = settings_for(dgr, cam, bg, deg, dev)
+    with torch.no_grad():
+        R, color, radii, geom, binning, img = dgr._forward_native(
+            gs["means3D"], gs["shs"], None, gs["opacities"], gs["scales"], gs["rotations"], None, rs,
+            rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+        f = ref.forward(gs["means3D"], gs["opacities"], rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg, W, H,
+                        cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], deg)
+    torch.cuda.synchronize()
+    assert R == f["num_rendered"]
+    assert torch.equal(radii, f["radii"])
+    mg, rg = ws_decode.decode_geom(geom, P), ref.decode_geom(f["geom"], P)
+    vis = (radii > 0).cpu()
+    assert torch.equal(mg["tiles_touched"], rg["tiles_touched"])
+    for k in ("means2D", "depths", "conic_opacity", "rgb"):
+        a, b = mg[k][vis], rg[k][vis]
+        assert torch.equal(a, b) or rel_err(a, b) < 1e-6, (k, rel_err(a, b))
+    assert torch.equal(mg["depths"][vis], rg["depths"][vis]), "depth bits feed the sort key"
+    assert torch.equal(mg["clamped"][vis], rg["clamped"][vis].bool())
+    mb, rb = ws_decode.decode_binning(binning, R), ref.decode_binning(f["binning"], R)
+    assert torch.equal(mb["keys"], rb["keys"])
+    assert torch.equal(mb["point_list"], rb["point_list"])
+    mi, ri = ws_decode.decode_img(img, W, H), ref.decode_img(f["img"], W, H)
+    T = mi["ranges"].shape[0]
+    assert torch.equal(mi["ranges"], ri["ranges"][:T])
+    assert torch.equal(mi["n_contrib"], ri["n_contrib"])
+    assert rel_err(mi["final_T"], ri["final_T"]) < 1e-6
+    assert rel_err(color, f["color"]) < TOL
+
+
+@pytest.mark.parametrize("deg,mode", [(0, "sh"), (2, "sh"), (0, "colors")])
+def test_vs_cpu_oracle(dgr, deg, mode):
+    from oracle import gs_oracle as O
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 800, 80, 56
+    gs, cam, dL, bg = scene_on(dev, P, W, H, 11, deg)
+    bg = torch.tensor([0.2, 0.5, 0.7], device=dev)
+    rs = settings_for(dgr, cam, bg, deg, dev)
+    c1, r1, g1 = _run(_ours(dgr), gs, rs, dL, mode)
+    cpu = {k: v.cpu() for k, v in gs.items()}
+    colors = (cpu["shs"][:, 0] * 0.28209479177387814 + 0.5).clamp(min=0) if mode == "colors" else None
+    pre, binning, fwd = O.rasterize_forward(cpu["means3D"], cpu["opacities"], cam.viewmatrix, cam.projmatrix,
+                                            cam.campos, bg.cpu(), W, H, cam.tanfovx, cam.tanfovy, cpu["scales"],
+                                            cpu["rotations"], 1.0, None, None if colors is not None else cpu["shs"],
+                                            deg, colors)
+    g = O.rasterize_backward(dL.cpu(), pre, binning, fwd, cpu["means3D"], cam.viewmatrix, cam.projmatrix, cam.campos,
+                             bg.cpu(), W, H, cam.tanfovx, cam.tanfovy, cpu["scales"], cpu["rotations"], 1.0, None,
+                             None if colors is not None else cpu["shs"], deg)
+    assert torch.equal(r1.cpu(), pre["radii"])
+    assert rel_err(c1, fwd["color"]) < TOL
+    assert rel_err(g1["means3D"], g["dL_dmeans3D"]) < 2e-4
+    assert rel_err(g1["scales"], g["dL_dscales"]) < 2e-4
+    assert rel_err(g1["rotations"], g["dL_drotations"]) < 2e-4
+    assert rel_err(g1["opacities"], g["dL_dopacity"]) < 2e-4
+    assert rel_err(g1["means2D"], g["dL_dmeans2D"]) < 2e-4
+    if mode == "sh":
+        assert rel_err(g1["shs"], g["dL_dsh"]) < 2e-4
+    else:
+        assert rel_err(g1["colors"], g["dL_dcolors"]) < 2e-4
+
+
+def test_cov3d_precomp_path(dgr, ref):
+    from oracle import gs_oracle as O
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 4000, 160, 112
+    gs, cam, dL, bg = scene_on(dev, P, W, H, 21, 0)
+    rs = settings_for(dgr, cam, bg, 0, dev)
+    cov = O.cov3d_from_scale_rot(gs["scales"].cpu(), 1.0, gs["rotations"].cpu()).to(dev)
+    outs = []
+    for fn in (_ours(dgr), _theirs(ref)):
+        m = gs["means3D"].clone().requires_grad_(True)
+        c = cov.clone().requires_grad_(True)
+        o = gs["opacities"].clone().requires_grad_(True)
+        s = gs["shs"].clone().requires_grad_(True)
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, radii = fn(m, m2, o, rs, shs=s, cov3D_precomp=c)
+        (color * dL).sum().backward()
+        outs.append((color.detach(), radii, m.grad, c.grad, o.grad, s.grad))
+    assert torch.equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][2:], outs[1][2:]):
+        assert rel_err(a, b) < TOL
+    assert rel_err(outs[0][0], outs[1][0]) < TOL
+
+
+def test_rotated_cameras_and_scale_modifier(dgr, ref):
+    import gsr_synth as S
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 30000, 320, 240
+    gs, _, dL, bg = scene_on(dev, P, W, H, 31, 1)
+    for cam in S.orbit_cameras(W, H, 3, (0.0, 0.0, 4.0), 0.5):
+        rs = settings_for(dgr, cam, bg, 1, dev, scale_modifier=0.7)
+        c1, r1, g1 = _run(_ours(dgr), gs, rs, dL, "sh")
+        c2, r2, g2 = _run(_theirs(ref), gs, rs, dL, "sh")
+        assert torch.equal(r1, r2)
+        assert rel_err(c1, c2) < TOL
+        for k in g2:
+            assert rel_err(g1[k], g2[k]) < TOL, k
+
+
+def test_edge_cases(dgr):
+    from tests.util import scene_on, settings_for
+    dev = torch.device("cuda:0")
+    W, H = 48, 32
+    gs, cam, dL, bg = scene_on(dev, 64, W, H, 5, 0)
+    bg = torch.tensor([0.25, 0.5, 0.75], device=dev)
+    rs = settings_for(dgr, cam, bg, 0, dev)
+    rast = dgr.GaussianRasterizer(rs)
+    # P == 0 -> zero image (reference: DGR/rasterize_points.cu:81), empty radii
+    e = {k: v[:0] for k, v in gs.items()}
+    color, radii = rast(means3D=e["means3D"], means2D=torch.zeros(0, 3, device=dev), opacities=e["opacities"],
+                        shs=e["shs"], scales=e["scales"], rotations=e["rotations"])
+    assert color.shape == (3, H, W) and float(color.abs().max()) == 0.0 and radii.numel() == 0
+    # everything behind the camera -> background only, all radii 0, zero grads
+    m = gs["means3D"].clone()
+    m[:, 2] = -1.0
+    m.requires_grad_(True)
+    color, radii = rast(means3D=m, means2D=torch.zeros(64, 3, device=dev), opacities=gs["opacities"], shs=gs["shs"],
+                        scales=gs["scales"], rotations=gs["rotations"])
+    assert int(radii.abs().sum()) == 0
+    assert torch.allclose(color, bg[:, None, None].expand_as(color))
+    color.sum().backward()
+    assert float(m.grad.abs().max()) == 0.0
+    # argument validation mirrors the reference
+    with pytest.raises(Exception):
+        rast(means3D=gs["means3D"], means2D=None, opacities=gs["opacities"], scales=gs["scales"], rotations=gs["rotations"])
+    with pytest.raises(Exception):
+        rast(means3D=gs["means3D"], means2D=None, opacities=gs["opacities"], shs=gs["shs"], scales=gs["scales"])
+    with pytest.raises(RuntimeError):
+        rast(means3D=gs["means3D"].reshape(-1), means2D=None, opacities=gs["opacities"], shs=gs["shs"],
+             scales=gs["scales"], rotations=gs["rotations"])
+    # markVisible == near-plane test
+    vis = rast.markVisible(gs["means3D"])
+    assert torch.equal(vis, gs["means3D"][:, 2] > 0.1)
+
+
+def test_camera_gradients(dgr):
+    """Extension a17: dL/d{viewmatrix, projmatrix, campos} against fp64 autograd through the oracle."""
+    import gsr_synth as S
+    from oracle import gs_oracle as O
+    from tests.util import rel_err, settings_for
+    dev = torch.device("cuda:0")
+    W, H, deg = 64, 48, 2
+    gs, _, dL, _ = S.make_scene(300, W, H, seed=3, sh_degree=deg)
+    gs["opacities"] = gs["opacities"] * 0.6          # keep alpha below the 0.99 clamp (see oracle docstring)
+    cam = S.orbit_cameras(W, H, 3, (0.0, 0.0, 4.0), 0.5)[1]
+    bg = torch.tensor([0.2, 0.5, 0.7])
+    dt = torch.float64
+    view = cam.viewmatrix.to(dt).clone().requires_grad_(True)
+    proj = cam.projmatrix.to(dt).clone().requires_grad_(True)
+    campos = cam.campos.to(dt).clone().requires_grad_(True)
+    img = O.differentiable_render(gs["means3D"].to(dt), gs["opacities"].to(dt), gs["scales"].to(dt),
+                                  gs["rotations"].to(dt), gs["shs"].to(dt), deg, view, proj, campos, bg, W, H,
+                                  cam.tanfovx, cam.tanfovy)
+    (img * dL.to(dt)).sum().backward()
+    v = cam.viewmatrix.to(dev).requires_grad_(True)
+    p = cam.projmatrix.to(dev).requires_grad_(True)
+    c = cam.campos.to(dev).requires_grad_(True)
+    rs = dgr.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg.to(dev), 1.0, v, p, deg, c, False, False)
+    d = {k: t.to(dev) for k, t in gs.items()}
+    color, _ = dgr.GaussianRasterizer(rs)(means3D=d["means3D"], means2D=torch.zeros(300, 3, device=dev),
+                                          opacities=d["opacities"], shs=d["shs"], scales=d["scales"],
+                                          rotations=d["rotations"])
+    (color * dL.to(dev)).sum().backward()
+    assert rel_err(color, img) < TOL
+    assert rel_err(v.grad, view.grad) < 1e-3
+    assert rel_err(p.grad, proj.grad) < 1e-3
+    assert rel_err(c.grad, campos.grad) < 1e-3

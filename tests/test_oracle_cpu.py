@@ -1,0 +1,68 @@
+"""CPU tests of the oracle itself: its analytic backward (the reference's hand-written derivative,
+restated) against fp64 autograd through a differentiable restatement of the forward, and internal
+consistency of binning.  (The oracle-vs-reference pin lives in test_oracle_golden.py.)"""
+import torch
+
+import gsr_synth as S
+from oracle import gs_oracle as O
+
+
+def _scene(P=300, W=64, H=48, deg=2, seed=3):
+    gs, _, dL, _ = S.make_scene(P, W, H, seed=seed, sh_degree=deg)
+    gs["opacities"] = gs["opacities"] * 0.6   # stay below the alpha clamp: the reference ignores it in backward
+    cam = S.orbit_cameras(W, H, 3, (0.0, 0.0, 4.0), 0.5)[1]
+    return gs, cam, dL, torch.tensor([0.2, 0.5, 0.7])
+
+
+def test_analytic_backward_matches_autograd_fp64():
+    W, H, deg = 64, 48, 2
+    gs, cam, dL, bg = _scene(300, W, H, deg)
+    dt = torch.float64
+    leaf = {k: v.to(dt).clone().requires_grad_(True) for k, v in gs.items()}
+    img = O.differentiable_render(leaf["means3D"], leaf["opacities"], leaf["scales"], leaf["rotations"], leaf["shs"],
+                                  deg, cam.viewmatrix, cam.projmatrix, cam.campos, bg, W, H, cam.tanfovx, cam.tanfovy)
+    (img * dL.to(dt)).sum().backward()
+    pre, binning, fwd = O.rasterize_forward(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix, cam.campos,
+                                            bg, W, H, cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0,
+                                            None, gs["shs"], deg, dtype=dt)
+    assert float((img.detach() - fwd["color"]).abs().max()) < 1e-12
+    g = O.rasterize_backward(dL, pre, binning, fwd, gs["means3D"], cam.viewmatrix, cam.projmatrix, cam.campos, bg, W,
+                             H, cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], deg,
+                             dtype=dt)
+    for name, key in (("means3D", "dL_dmeans3D"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                      ("opacities", "dL_dopacity"), ("shs", "dL_dsh")):
+        a, b = g[key], leaf[name].grad
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-6, name
+
+
+def test_fp32_oracle_close_to_fp64():
+    W, H, deg = 64, 48, 1
+    gs, cam, dL, bg = _scene(400, W, H, deg, seed=8)
+    outs = []
+    for dt in (torch.float32, torch.float64):
+        pre, binning, fwd = O.rasterize_forward(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix,
+                                                cam.campos, bg, W, H, cam.tanfovx, cam.tanfovy, gs["scales"],
+                                                gs["rotations"], 1.0, None, gs["shs"], deg, dtype=dt)
+        outs.append((pre, binning, fwd))
+    assert torch.equal(outs[0][0]["radii"], outs[1][0]["radii"])
+    assert torch.equal(outs[0][1]["point_list"], outs[1][1]["point_list"])
+    assert float((outs[0][2]["color"].double() - outs[1][2]["color"]).abs().max()) < 1e-4
+
+
+def test_binning_invariants():
+    W, H = 100, 70                      # ragged tile grid 7 x 5
+    gs, cam, dL, bg = S.make_scene(2000, W, H, seed=4)
+    pre = O.preprocess(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix, cam.campos, W, H, cam.tanfovx,
+                       cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], 0)
+    b = O.bin_and_sort(pre, W, H)
+    keys = b["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())                       # sortedness
+    assert b["num_rendered"] == int(pre["tiles_touched"].sum())
+    assert int((b["ranges"][:, 1] - b["ranges"][:, 0]).sum()) == b["num_rendered"]
+    # ties keep ascending Gaussian index (stable sort)
+    same = keys[1:] == keys[:-1]
+    assert bool((b["point_list"][1:][same] > b["point_list"][:-1][same]).all())
+    # culled Gaussians (behind the near plane) never appear
+    behind = gs["means3D"][:, 2] <= 0.1
+    assert int(pre["radii"][behind].abs().sum()) == 0
+    assert not bool(torch.isin(b["point_list"], torch.nonzero(behind).reshape(-1)).any())
