@@ -151,7 +151,7 @@ long long gsr_launch_count(void);
 
 /* Introspection for tests (sub-buffers of the opaque workspaces; byte offsets from the base). */
 typedef struct gsr_geom_layout {
-    size_t rec;           /* float4[3P]: (px,py,depth,lam_max) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
+    size_t rec;           /* float4[3P]: (px,py,depth,cull_r2) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
     size_t tiles_touched; /* uint32[P] */
     size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched */
     size_t scan_temp;     /* scan scratch */

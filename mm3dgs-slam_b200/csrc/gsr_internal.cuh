@@ -14,7 +14,7 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 
 // ---- per-Gaussian state ---------------------------------------------------------------------
 // One 48-byte record per Gaussian so that the blend kernels gather a single contiguous chunk:
-//   rec[3i+0] = (px, py, depth, lam_max)        pixel mean, view depth, larger cov2D eigenvalue
+//   rec[3i+0] = (px, py, depth, cull_r2)        pixel mean, view depth, conservative cull radius^2
 //   rec[3i+1] = (conic.x, conic.y, conic.z, opacity)
 //   rec[3i+2] = (r, g, b, bits)                 bits: SH clamp flags (bit ch set => channel clamped)
 // The reference keeps these in separate arrays (GeometryState, CR/rasterizer_impl.h:29-44) and

@@ -61,6 +61,20 @@ __device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* 
     }
 }
 
+// Conservative squared radius (pixels^2) outside of which the splat cannot reach alpha >= 1/255:
+//   alpha = o*exp(power) >= 1/255  =>  power >= -ln(255 o),   power <= -|d|^2 / (2 lam_max)
+//   =>  |d|^2 <= 2 lam_max ln(255 o).
+// 3% + 0.5 px^2 slack covers the rounding of the conic and of the power evaluation; for very large
+// splats (lam_max > 1000 px^2) the relative error of the evaluated power is no longer negligible
+// against that slack, so they are never culled (+inf).  Used only to SKIP work in the blend kernels;
+// it never changes which (pixel, splat) pairs contribute.
+__device__ __forceinline__ float cull_radius2(float lam_max, float opacity)
+{
+    if (!(lam_max <= 1000.f)) return __int_as_float(0x7f800000);
+    const float L = fmaxf(logf(255.f * opacity), 0.f);
+    return 2.06f * lam_max * L + 0.5f;   // NaN opacity -> NaN -> never culled (tests are !(d2 > r2))
+}
+
 // ----------------------------------------------------------------------------------------------
 // Forward
 // ----------------------------------------------------------------------------------------------
@@ -140,8 +154,9 @@ __global__ void __launch_bounds__(kPB) k_preprocess_fwd(PreArgs a)
                 cg = s_col[3 * tid + 1];
                 cb = s_col[3 * tid + 2];
             }
-            r0 = make_float4(o.px, o.py, o.depth, o.lam_max);
-            r1 = make_float4(o.cx, o.cy, o.cz, a.opac[idx]);
+            const float opacity = a.opac[idx];
+            r0 = make_float4(o.px, o.py, o.depth, cull_radius2(o.lam_max, opacity));
+            r1 = make_float4(o.cx, o.cy, o.cz, opacity);
             r2 = make_float4(cr, cg, cb, __int_as_float(bits));
         }
         a.radii[idx] = radius;
