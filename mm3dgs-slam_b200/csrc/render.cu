@@ -284,14 +284,22 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     v5 = G * dL_dalpha;
                 }
                 if (__any_sync(kFull, live)) {
-                    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
-                    v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
-                    v6 = warp_sum(v6); v7 = warp_sum(v7); v8 = warp_sum(v8);
-                    if (lane == 0) {
-                        atomicAdd(&s_acc[0][j], v0); atomicAdd(&s_acc[1][j], v1); atomicAdd(&s_acc[2][j], v2);
-                        atomicAdd(&s_acc[3][j], v3); atomicAdd(&s_acc[4][j], v4); atomicAdd(&s_acc[5][j], v5);
-                        atomicAdd(&s_acc[6][j], v6); atomicAdd(&s_acc[7][j], v7); atomicAdd(&s_acc[8][j], v8);
-                    }
+                    // Transposing butterfly: 8 terms reduced over 32 lanes with 4+2+1+1+1 shuffles
+                    // (instead of 8x5); lane 4*k ends up holding the warp total of term k.
+                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                    float a0 = (b4 ? v4 : v0) + __shfl_xor_sync(kFull, b4 ? v0 : v4, 16);
+                    float a1 = (b4 ? v5 : v1) + __shfl_xor_sync(kFull, b4 ? v1 : v5, 16);
+                    float a2 = (b4 ? v6 : v2) + __shfl_xor_sync(kFull, b4 ? v2 : v6, 16);
+                    float a3 = (b4 ? v7 : v3) + __shfl_xor_sync(kFull, b4 ? v3 : v7, 16);
+                    float c0 = (b3 ? a2 : a0) + __shfl_xor_sync(kFull, b3 ? a0 : a2, 8);
+                    float c1 = (b3 ? a3 : a1) + __shfl_xor_sync(kFull, b3 ? a1 : a3, 8);
+                    float e0 = (b2 ? c1 : c0) + __shfl_xor_sync(kFull, b2 ? c0 : c1, 4);
+                    e0 += __shfl_xor_sync(kFull, e0, 2);
+                    e0 += __shfl_xor_sync(kFull, e0, 1);
+                    v8 = warp_sum(v8);
+                    // term index held by this lane group: 4*b4 + 2*b3 + b2
+                    if ((lane & 3) == 0) atomicAdd(&s_acc[lane >> 2][j], e0);
+                    if (lane == 1) atomicAdd(&s_acc[8][j], v8);
                     touched |= 1u << b;
                 }
             }

@@ -1,0 +1,78 @@
+"""Multi-rank host logic of the keyframe-sharded map step on CPU (gloo, world_size 2):
+sharded step == single-rank gradient accumulation over the same keyframes, and the bucket is what
+the collective runs on (no gather copy).  The per-keyframe render here is the CPU oracle's
+differentiable forward (test infrastructure) — the product rasterizer has no CPU path."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gsr_synth as S
+from gsr_mapstep import GradBucket, ShardedMapStep, shard_keyframes
+
+
+def _scene():
+    W, H = 32, 32
+    gs, _, dL, _ = S.make_scene(60, W, H, seed=5, sh_degree=0)
+    cams = S.orbit_cameras(W, H, 4, (0.0, 0.0, 4.0), 0.3)
+    return gs, cams, dL, W, H
+
+
+def _frame_fn(dL, W, H):
+    from oracle import gs_oracle as O
+
+    def f(p, cam):
+        img = O.differentiable_render(p["means3D"], p["opacities"], p["scales"], p["rotations"], p["shs"], 0,
+                                      cam.viewmatrix, cam.projmatrix, cam.campos, torch.zeros(3), W, H, cam.tanfovx,
+                                      cam.tanfovy)
+        (img * dL.double()).sum().backward()
+        return img.detach()
+    return f
+
+
+def _params(gs):
+    return {k: gs[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gs, cams, dL, W, H = _scene()
+    step = ShardedMapStep(_params(gs), _frame_fn(dL, W, H))
+    step.step(cams)
+    if rank == 0:
+        torch.save(step.bucket.flat.clone(), out)
+    dist.destroy_process_group()
+
+
+def test_shard_assignment():
+    assert shard_keyframes(8, 0, 8) == [0] and shard_keyframes(8, 3, 4) == [3, 7]
+    assert shard_keyframes(3, 3, 4) == []          # idle rank still joins the all-reduce
+    assert sorted(sum((shard_keyframes(11, r, 4) for r in range(4)), [])) == list(range(11))
+
+
+def test_bucket_views_alias_flat():
+    gs, *_ = _scene()
+    p = _params(gs)
+    b = GradBucket(p)
+    assert b.flat.numel() == sum(v.numel() for v in p.values()) == 60 * 14     # 56 B per Gaussian at SH-0
+    p["scales"].grad.add_(1.0)
+    assert float(b.flat.sum()) == 60 * 3
+    assert p["means3D"].grad.data_ptr() == b.flat.data_ptr()
+
+
+def test_sharded_equals_accumulated(tmp_path):
+    gs, cams, dL, W, H = _scene()
+    single = ShardedMapStep(_params(gs), _frame_fn(dL, W, H))
+    single.step(cams)
+    ref = single.bucket.flat.clone()
+    assert float(ref.abs().max()) > 0
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "bucket.pt")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6 * float(ref.abs().max()))
