@@ -124,10 +124,8 @@ def stage_bytes(P, R, N, M=1):
     g_in = 44 + 12 * M
     return {
         "preprocess_fwd": (g_in + 48) * P,
-        "scan": 8 * P,
-        "duplicate": 12 * R,
-        "sort": 24 * R,
-        "tile_ranges": 8 * R,
+        "depth_sort": 8 * P,                       # SURVEY's "scan" row: the per-Gaussian ordering pass
+        "tile_partition": (12 + 24 + 8) * R,       # duplicate + ideal sort + range rows
         "render_fwd": 40 * R + 20 * N,
         "render_bwd": 76 * R + 20 * N,
         "preprocess_bwd": (g_in + 36 + 48 + g_in) * P,

@@ -108,22 +108,23 @@ int gsr_abi_version(void);
 const char* gsr_last_error(void);
 
 /* Workspace sizes in bytes.  geom: per-Gaussian state; img: per-pixel + per-tile state;
- * binning: sort keys/values for R tile instances (R = num_rendered). */
-size_t gsr_geom_ws_bytes(int32_t P);
+ * binning: the per-tile, depth-ordered Gaussian-id list of the R tile instances (R = num_rendered). */
+size_t gsr_geom_ws_bytes(int32_t P, int32_t width, int32_t height);
 size_t gsr_img_ws_bytes(int32_t width, int32_t height);
 size_t gsr_binning_ws_bytes(int64_t R);
 
-/* Forward, phase 1: per-Gaussian projection / covariance / SH colour / tile counts and their
- * prefix sum.  Writes radii[P].  If num_rendered is not NULL the call synchronises `stream`
- * and stores R there (host memory) so the caller can size the binning workspace — this is the
- * one host sync of the reference (rasterizer_impl.cu:280-281).  The device copy of R stays in
- * geom_ws for phase 2. */
+/* Forward, phase 1: per-Gaussian projection / covariance / SH colour / tile rectangles, the
+ * instance count R, and the depth sort of the Gaussians.  Writes radii[P].  If num_rendered is not
+ * NULL the call waits (on an event recorded right after the projection kernel, not on the whole
+ * stream) and stores R there (host memory) so the caller can size the binning workspace — the one
+ * host hand-off the reference also has (rasterizer_impl.cu:280-281). */
 int gsr_forward_preprocess(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                            int32_t* radii, void* geom_ws, size_t geom_ws_bytes,
                            void* img_ws, size_t img_ws_bytes, int32_t* num_rendered);
 
-/* Forward, phase 2: tile-instance duplication, (tile|depth) sort, tile ranges, per-tile
- * front-to-back alpha compositing.  R must be the value phase 1 produced. */
+/* Forward, phase 2: stable partition of the tile instances by tile in depth order (== the
+ * reference's (tile|depth)-sorted list), tile ranges, per-tile front-to-back alpha compositing.
+ * R must be the value phase 1 produced. */
 int gsr_forward_render(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                        const int32_t* radii, int64_t R,
                        void* geom_ws, void* binning_ws, size_t binning_ws_bytes, void* img_ws,
@@ -151,15 +152,15 @@ long long gsr_launch_count(void);
 
 /* Introspection for tests (sub-buffers of the opaque workspaces; byte offsets from the base). */
 typedef struct gsr_geom_layout {
-    size_t rec;           /* float4[3P]: (px,py,depth,cull_r2) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
-    size_t tiles_touched; /* uint32[P] */
-    size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched */
-    size_t scan_temp;     /* scan scratch */
+    size_t rec;        /* float4[3P]: (px,py,depth,cull_r2) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
+    size_t rects;      /* ushort4[P]: tile rectangle {x0,y0,x1,y1}, empty for culled Gaussians */
+    size_t depth_keys; /* uint32[P]: float bits of the view depth, 0xFFFFFFFF for culled Gaussians */
+    size_t sorted_ids; /* uint32[P]: Gaussian ids in (depth, index) order, culled last */
     size_t total;
 } gsr_geom_layout;
 typedef struct gsr_img_layout { size_t final_T, n_contrib, ranges, total; } gsr_img_layout;
-typedef struct gsr_binning_layout { size_t point_list, keys, point_list_unsorted, keys_unsorted, sort_temp, total; } gsr_binning_layout;
-void gsr_geom_layout_of(int32_t P, gsr_geom_layout* out);
+typedef struct gsr_binning_layout { size_t point_list, total; } gsr_binning_layout;
+void gsr_geom_layout_of(int32_t P, int32_t width, int32_t height, gsr_geom_layout* out);
 void gsr_img_layout_of(int32_t width, int32_t height, gsr_img_layout* out);
 void gsr_binning_layout_of(int64_t R, gsr_binning_layout* out);
 

@@ -1,95 +1,431 @@
-// binning.cu — tile-instance generation, (tile|depth) ordering and per-tile ranges.
+// binning.cu — builds the per-tile, depth-ordered splat lists.
 //
-// Replaces cub::DeviceScan::InclusiveSum (CR/rasterizer_impl.cu:277), duplicateWithKeys
-// (:70-111), cub::DeviceRadixSort::SortPairs (:303-308) and identifyTileRanges (:116-138).
-// The produced (key, value) list is bit-identical to the reference's: key = tile << 32 | depth
-// bits, ascending, ties in ascending Gaussian index (stable LSD order).
+// Replaces cub::DeviceScan::InclusiveSum (CR/rasterizer_impl.cu:277), duplicateWithKeys (:70-111),
+// the 64-bit cub::DeviceRadixSort::SortPairs over all R tile instances (:303-308) and
+// identifyTileRanges (:116-138).  The result is the same list the reference produces — instances
+// ordered by (tile, depth bits, Gaussian index) — but it is built B200-first, without ever
+// materialising or sorting 64-bit (tile|depth) keys:
+//
+//   1. depth sort of the P Gaussians (not of the R >> P instances): stable LSD radix sort of the
+//      32-bit depth keys in three 11/11/10-bit passes (culled Gaussians carry key 0xFFFFFFFF and sink
+//      to the end).  Ties keep ascending Gaussian index — the reference's tie order, because its
+//      stable sort starts from instances emitted in index order.
+//   2. ONE stable multi-bin partition of the instances by tile id, walking the Gaussians in depth
+//      order: within a tile, instances therefore appear in (depth, index) order.
+//
+// Both steps are the same three-kernel pattern (count -> scan -> scatter) built around per-warp
+// 16-bit histograms in shared memory — the wide digits / thousands of tile bins are only possible
+// because a B200 CTA can hold 32-160 KB of counters next to its data:
+//   count   : CTA-local histogram of a contiguous chunk (shared-memory atomics), one row of H[c][bin]
+//   scan    : per bin, exclusive prefix over the chunks (+ per-bin totals)
+//   scatter : exclusive scan over the bins (in shared memory), then each warp ranks its contiguous
+//             sub-chunk with __match_any_sync, in order, against its private counters.
+// HBM traffic: 3 x 16 B per Gaussian for the depth sort + 4 B per instance written once, instead of
+// the reference's ~150 B per instance (6 onesweep passes over 12-byte pairs).
 #include "gsr_internal.cuh"
-#include "gsr_math.cuh"
-#include <cub/cub.cuh>
 
 namespace gsr {
 
-size_t scan_temp_bytes(int P)
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kDigitBits = 11;
+constexpr int kBins = 1 << kDigitBits;       // 2048
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 16;               // keys per thread
+constexpr int kSortChunk = kSortThreads * kSortItems;   // 4096 keys per CTA
+
+int sort_chunks(int P) { return (P + kSortChunk - 1) / kSortChunk; }
+
+__device__ __forceinline__ unsigned lanemask_lt()
 {
-    size_t n = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, n, (uint32_t*)nullptr, (uint32_t*)nullptr, P > 0 ? P : 1);
-    return n;
-}
-size_t sort_temp_bytes(int64_t R)
-{
-    size_t n = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, n, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, R > 0 ? (int)R : 1);
-    return n;
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
 }
 
-void launch_scan(const uint32_t* in, uint32_t* out, int P, char* temp, size_t temp_bytes, cudaStream_t s)
+// Exclusive scan of `n` u32 values in shared memory (n a multiple of blockDim.x, in place), all threads call.
+// Each thread owns n/blockDim consecutive values.  `s_warp` is scratch for blockDim/32 partials.
+template <int PER_THREAD>
+__device__ __forceinline__ void block_exclusive_scan(uint32_t* s_data, uint32_t* s_warp)
 {
-    if (P <= 0) return;
-    cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, P, s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[PER_THREAD];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; i++) {
+        v[i] = s_data[tid * PER_THREAD + i];
+        sum += v[i];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += s_warp[w];
+    uint32_t run = wbase + incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; i++) {
+        s_data[tid * PER_THREAD + i] = run;
+        run += v[i];
+    }
+    __syncthreads();
 }
 
-// One warp per 32 Gaussians; each lane owns one Gaussian and walks its tile rectangle.
-__global__ void __launch_bounds__(256) k_duplicate(int P, const float4* __restrict__ rec, const int* __restrict__ radii,
-                                                   const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
-                                                   uint32_t* __restrict__ vals, int gx, int gy)
+// ================================================================================================
+// 1. Depth sort (P keys)
+// ================================================================================================
+__global__ void __launch_bounds__(kSortThreads) k_digit_count(const uint32_t* __restrict__ keys, int n, int shift,
+                                                              uint32_t mask, uint32_t* __restrict__ hist)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int r = radii[idx];
-    if (r <= 0) return;
-    const float4 r0 = rec[(size_t)idx * 3];
-    uint32_t off = (idx == 0) ? 0u : offsets[idx - 1];
-    int x0, y0, x1, y1;
-    tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
-    const uint64_t depth_bits = (uint64_t)__float_as_uint(r0.z);
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            uint64_t key = (uint64_t)(uint32_t)(y * gx + x);
-            key = (key << 32) | depth_bits;
-            keys[off] = key;
-            vals[off] = (uint32_t)idx;
-            off++;
+    __shared__ uint32_t s_hist[kBins];
+    const int tid = threadIdx.x;
+    for (int b = tid; b < kBins; b += kSortThreads) s_hist[b] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kSortChunk;
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+        const int i = base + j * kSortThreads + tid;
+        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    uint32_t* row = hist + (size_t)blockIdx.x * kBins;
+    for (int b = tid; b < kBins; b += kSortThreads) row[b] = s_hist[b];
+}
+
+// Column scan of H[chunks][bins]: in place H[c][b] <- sum_{c' < c} H[c'][b]; totals[b] <- sum_c H[c][b].
+// One CTA per 32 bins; the chunk axis is split into 8 segments handled by the 8 warps.
+__global__ void __launch_bounds__(256) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
+                                                     uint32_t* __restrict__ totals)
+{
+    __shared__ uint32_t s_seg[8][32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const int per = (chunks + 7) / 8;
+    const int c0 = min(seg * per, chunks), c1 = min(c0 + per, chunks);
+    uint32_t sum = 0;
+    if (b < bins)
+        for (int c = c0; c < c1; c++) sum += hist[(size_t)c * bins + b];
+    s_seg[seg][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int s = 0; s < seg; s++) run += s_seg[s][lane];
+    if (b < bins) {
+        for (int c = c0; c < c1; c++) {
+            const size_t o = (size_t)c * bins + b;
+            const uint32_t v = hist[o];
+            hist[o] = run;
+            run += v;
         }
+        if (seg == 7) totals[b] = run;
+    }
 }
 
-void launch_duplicate(int P, const float4* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
-                      uint32_t* vals, int gx, int gy, cudaStream_t s)
+// Stable scatter of one digit pass.  vals_in == nullptr means "value = element index" (first pass).
+__global__ void __launch_bounds__(kSortThreads) k_digit_scatter(const uint32_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in, int n, int shift,
+                                                                uint32_t mask, const uint32_t* __restrict__ base,
+                                                                const uint32_t* __restrict__ totals,
+                                                                uint32_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ vals_out)
 {
-    if (P <= 0) return;
-    k_duplicate<<<(P + 255) / 256, 256, 0, s>>>(P, rec, radii, offsets, keys, vals, gx, gy);
-}
+    __shared__ uint32_t s_start[kBins];               // absolute start of this CTA's run, per bin
+    __shared__ uint16_t s_cnt[kSortWarps][kBins];     // per-warp counters / running offsets
+    __shared__ uint32_t s_scan[kSortWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-void launch_sort(BinWS& b, int64_t R, int end_bit, cudaStream_t s)
-{
-    if (R <= 0) return;
-    cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys, b.point_list_unsorted,
-                                    b.point_list, (int)R, 0, end_bit, s);
-}
+    for (int b = tid; b < kBins; b += kSortThreads) s_start[b] = totals[b];
+    for (int i = tid; i < kSortWarps * kBins / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    block_exclusive_scan<kBins / kSortThreads>(s_start, s_scan);    // bin starts over the whole array
+    const uint32_t* row = base + (size_t)blockIdx.x * kBins;
+    for (int b = tid; b < kBins; b += kSortThreads) s_start[b] += row[b];
+    // (visibility of s_start to the other warps is covered by the barrier after the counting sweep)
 
-__global__ void __launch_bounds__(256) k_tile_ranges(int64_t R, const uint64_t* __restrict__ keys, uint2* ranges)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t cur = (uint32_t)(keys[i] >> 32);
-    if (i == 0)
-        ranges[cur].x = 0;
-    else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-        if (cur != prev) {
-            ranges[prev].y = (uint32_t)i;
-            ranges[cur].x = (uint32_t)i;
+    // each warp owns a contiguous sub-chunk; lanes hold consecutive elements of each 32-element batch
+    const int wbase = blockIdx.x * kSortChunk + warp * (kSortChunk / kSortWarps);
+    uint32_t key[kSortItems];
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+        const int i = wbase + j * 32 + lane;
+        key[j] = (i < n) ? keys_in[i] : 0u;
+    }
+    // counting sweep
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+        const int i = wbase + j * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(kFullMask, d);
+        if (valid && (peers & lanemask_lt()) == 0) s_cnt[warp][d] += (uint16_t)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over the warps, per bin
+    for (int b = tid; b < kBins; b += kSortThreads) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            const uint32_t t = s_cnt[w][b];
+            s_cnt[w][b] = (uint16_t)run;
+            run += t;
         }
     }
-    if (i == R - 1) ranges[cur].y = (uint32_t)R;
+    __syncthreads();
+    // ranking sweep
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+        const int i = wbase + j * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(kFullMask, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = s_cnt[warp][d];
+            s_cnt[warp][d] = (uint16_t)(old + __popc(peers));
+        }
+        old = __shfl_sync(kFullMask, old, leader);
+        if (valid) {
+            const uint32_t pos = s_start[d] + old + __popc(peers & lanemask_lt());
+            keys_out[pos] = key[j];
+            vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
+        }
+        __syncwarp();
+    }
 }
 
-void launch_tile_ranges(int64_t R, const uint64_t* keys, uint2* ranges, int tiles, cudaStream_t s)
+void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s)
 {
-    cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s);
-    if (R <= 0) return;
-    k_tile_ranges<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys, ranges);
+    if (P <= 0) return;
+    const int C = sort_chunks(P);
+    const uint32_t* kin = depth_keys;
+    const uint32_t* vin = nullptr;
+    uint32_t* kout[3] = {w.keys_a, w.keys_b, w.keys_a};
+    uint32_t* vout[3] = {w.vals_a, w.vals_b, w.vals_a};
+    const int shifts[3] = {0, 11, 22};
+    const uint32_t masks[3] = {2047u, 2047u, 1023u};
+    for (int p = 0; p < 3; p++) {
+        k_digit_count<<<C, kSortThreads, 0, s>>>(kin, P, shifts[p], masks[p], w.hist);
+        k_column_scan<<<kBins / 32, 256, 0, s>>>(w.hist, C, kBins, w.totals);
+        k_digit_scatter<<<C, kSortThreads, 0, s>>>(kin, vin, P, shifts[p], masks[p], w.hist, w.totals, kout[p], vout[p]);
+        kin = kout[p];
+        vin = vout[p];
+    }
+    // result: w.keys_a / w.vals_a (depth-ordered keys and Gaussian ids)
+}
+
+// ================================================================================================
+// 2. Tile partition (R instances, generated on the fly from the depth-ordered Gaussians)
+// ================================================================================================
+// Walks `cnt` flattened instances of the 32 Gaussians held by the lanes of a warp (lane l owns a
+// rect of n_l = w_l*h_l tiles), 32 instances per step in lane-major order, and calls f(tile, src_lane)
+// on each valid instance.  `packed` = x0 | y0 << 10 | w << 20 per lane (x0,y0 < 1024, w < 4096).
+template <typename F>
+__device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t n_l, int gx, F&& f)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t incl = n_l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+    for (uint32_t b = 0; b < total; b += 32) {
+        const uint32_t i = b + lane;
+        const bool valid = i < total;
+        // source lane = number of lanes whose inclusive count is <= i
+        int src = 0;
+#pragma unroll
+        for (int stepw = 16; stepw > 0; stepw >>= 1) {
+            const uint32_t probe = __shfl_sync(kFullMask, incl, src + stepw - 1);
+            if (probe <= i) src += stepw;
+        }
+        src = min(src, 31);
+        const uint32_t s_incl = __shfl_sync(kFullMask, incl, src);
+        const uint32_t s_n = __shfl_sync(kFullMask, n_l, src);
+        const uint32_t s_pk = __shfl_sync(kFullMask, packed, src);
+        uint32_t tile = 0xffffffffu;
+        if (valid) {
+            const uint32_t k = i - (s_incl - s_n);
+            const uint32_t w = s_pk >> 20, x0 = s_pk & 1023u, y0 = (s_pk >> 10) & 1023u;
+            const uint32_t ry = k / w, rx = k - ry * w;
+            tile = (y0 + ry) * (uint32_t)gx + x0 + rx;
+        }
+        f(tile, src, valid);
+    }
+}
+
+__device__ __forceinline__ void load_rect(const uint32_t* __restrict__ perm, const ushort4* __restrict__ rects, int i,
+                                          int n, uint32_t& id, uint32_t& packed, uint32_t& cnt)
+{
+    id = 0;
+    packed = 1u << 20;
+    cnt = 0;
+    if (i < n) {
+        id = perm[i];
+        const ushort4 r = rects[id];
+        const uint32_t w = r.z - r.x, h = r.w - r.y;   // culled Gaussians store an empty rect
+        cnt = w * h;
+        packed = (uint32_t)r.x | ((uint32_t)r.y << 10) | ((w ? w : 1u) << 20);
+    }
+}
+
+// Dynamic shared memory: uint32 s_hist[T].
+__global__ void __launch_bounds__(256) k_tile_count(const uint32_t* __restrict__ perm, int n, int per_cta,
+                                                    const ushort4* __restrict__ rects, int gx, int T,
+                                                    uint32_t* __restrict__ hist)
+{
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* s_hist = s_dyn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int t = tid; t < T; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    const int c0 = blockIdx.x * per_cta, c1 = min(c0 + per_cta, n);
+    const int per_warp = (per_cta + nwarps - 1) / nwarps;
+    const int w0 = c0 + warp * per_warp, w1 = min(w0 + per_warp, c1);
+    for (int g0 = w0; g0 < w1; g0 += 32) {
+        uint32_t id, packed, cnt;
+        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
+        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int, bool valid) {
+            if (valid) atomicAdd(&s_hist[tile], 1u);
+        });
+    }
+    __syncthreads();
+    uint32_t* row = hist + (size_t)blockIdx.x * T;
+    for (int t = tid; t < T; t += blockDim.x) row[t] = s_hist[t];
+}
+
+// Exclusive scan of the per-tile totals -> ranges[t] = {start, end}.  Single CTA, any T.
+__global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict__ totals, int T, uint2* __restrict__ ranges,
+                                                      uint32_t* __restrict__ starts)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += 1024) {
+        const int t = t0 + tid;
+        const uint32_t v = (t < T) ? totals[t] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t x = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += s_warp[w];
+        const uint32_t carry = s_carry;
+        const uint32_t start = carry + wb + incl - v;
+        if (t < T) {
+            starts[t] = start;
+            ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + wb + incl;
+        __syncthreads();
+    }
+}
+
+// Dynamic shared memory: uint32 s_start[T]; uint16 s_cnt[nwarps][T].
+__global__ void __launch_bounds__(256) k_tile_scatter(const uint32_t* __restrict__ perm, int n, int per_cta,
+                                                      const ushort4* __restrict__ rects, int gx, int T,
+                                                      const uint32_t* __restrict__ base,
+                                                      const uint32_t* __restrict__ starts,
+                                                      uint32_t* __restrict__ point_list)
+{
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* s_start = s_dyn;
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + T);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t* row = base + (size_t)blockIdx.x * T;
+    for (int t = tid; t < T; t += blockDim.x) s_start[t] = starts[t] + row[t];
+    for (int i = tid; i < nwarps * T; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const int c0 = blockIdx.x * per_cta, c1 = min(c0 + per_cta, n);
+    const int per_warp = (per_cta + nwarps - 1) / nwarps;
+    const int w0 = c0 + warp * per_warp, w1 = min(w0 + per_warp, c1);
+    uint16_t* my = s_cnt + (size_t)warp * T;
+    // counting sweep
+    for (int g0 = w0; g0 < w1; g0 += 32) {
+        uint32_t id, packed, cnt;
+        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
+        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int, bool valid) {
+            const unsigned peers = __match_any_sync(kFullMask, tile);
+            if (valid && (peers & lanemask_lt()) == 0) my[tile] += (uint16_t)__popc(peers);
+            __syncwarp();
+        });
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) {
+        uint32_t run = 0;
+        for (int w = 0; w < nwarps; w++) {
+            const uint32_t c = s_cnt[(size_t)w * T + t];
+            s_cnt[(size_t)w * T + t] = (uint16_t)run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // ranking sweep
+    for (int g0 = w0; g0 < w1; g0 += 32) {
+        uint32_t id, packed, cnt;
+        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
+        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int src, bool valid) {
+            const unsigned peers = __match_any_sync(kFullMask, tile);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = my[tile];
+                my[tile] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(kFullMask, old, leader);
+            const uint32_t gid = __shfl_sync(kFullMask, id, src);
+            if (valid) point_list[s_start[tile] + old + __popc(peers & lanemask_lt())] = gid;
+            __syncwarp();
+        });
+    }
+}
+
+// Chunking of the tile partition: per-warp counters are 16 bit, so a warp may own at most 65535
+// Gaussians; the CTA count is capped so that the H matrix stays small.
+void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem_count, size_t& smem_scatter)
+{
+    warps = 8;
+    while (warps > 1 && (size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024) warps >>= 1;
+    const int max_ctas = 4 * 148;
+    per_cta = 2048;
+    if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
+    per_cta = (per_cta + 31) / 32 * 32;
+    ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
+    smem_count = (size_t)T * 4;
+    smem_scatter = (size_t)T * (4 + 2 * (size_t)warps);
+}
+
+int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
+                          uint32_t* point_list, cudaStream_t s)
+{
+    const int T = gx * gy;
+    int ctas, per_cta, warps;
+    size_t smem_c, smem_s;
+    tile_partition_plan(P, T, ctas, per_cta, warps, smem_c, smem_s);
+    if (smem_s > 220 * 1024 || per_cta / warps > 65535) return -1;   // image / scene too large for this scheme
+    if (smem_s > 48 * 1024) {   // opt in to the large B200 carve-out (per device, cheap host call)
+        cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    }
+    k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist);
+    k_column_scan<<<(T + 31) / 32, 256, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals);
+    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts);
+    k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist, w.tile_starts,
+                                                    point_list);
+    return 0;
 }
 
 }  // namespace gsr

@@ -17,9 +17,9 @@ static thread_local std::string g_err;
 
 // ---- optional stage profiler (off by default; CUDA events on the caller's stream) -----------------
 // Stage ids are stable and named by gsr_profile_stage_name().
-enum Stage { ST_BEGIN = -1, ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_RANGES, ST_RENDER, ST_RENDER_BWD,
+enum Stage { ST_BEGIN = -1, ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_TILE_PARTITION, ST_RENDER, ST_RENDER_BWD,
              ST_PREPROCESS_BWD, ST_COUNT };
-static const char* kStageNames[ST_COUNT] = {"preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges", "render_fwd",
+static const char* kStageNames[ST_COUNT] = {"preprocess_fwd", "depth_sort", "tile_partition", "render_fwd",
                                             "render_bwd", "preprocess_bwd"};
 static std::atomic<int> g_prof_on{0};
 static std::atomic<long long> g_launches{0};
@@ -77,16 +77,28 @@ static T* carve(char*& p, size_t count)
     return r;
 }
 
-GeomWS geom_ws_carve(char* base, int P)
+GeomWS geom_ws_carve(char* base, int P, int W, int H)
 {
     GeomWS w;
     char* p = base;
     const size_t n = P > 0 ? (size_t)P : 1;
+    const int T = ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
     w.rec = carve<float4>(p, n * 3);
-    w.tiles_touched = carve<uint32_t>(p, n);
-    w.point_offsets = carve<uint32_t>(p, n);
-    w.scan_temp_bytes = scan_temp_bytes(P);
-    w.scan_temp = carve<char>(p, w.scan_temp_bytes);
+    w.rects = carve<ushort4>(p, n);
+    w.depth_keys = carve<uint32_t>(p, n);
+    w.counters = carve<uint32_t>(p, 64);
+    w.sort.keys_a = carve<uint32_t>(p, n);
+    w.sort.vals_a = carve<uint32_t>(p, n);
+    w.sort.keys_b = carve<uint32_t>(p, n);
+    w.sort.vals_b = carve<uint32_t>(p, n);
+    w.sort.hist = carve<uint32_t>(p, (size_t)sort_chunks((int)n) * 2048);
+    w.sort.totals = carve<uint32_t>(p, 2048);
+    int ctas, per_cta, warps;
+    size_t sc, ss;
+    tile_partition_plan((int)n, T, ctas, per_cta, warps, sc, ss);
+    w.sort.tile_hist = carve<uint32_t>(p, (size_t)ctas * T);
+    w.sort.tile_totals = carve<uint32_t>(p, (size_t)T);
+    w.sort.tile_starts = carve<uint32_t>(p, (size_t)T);
     w.total = (size_t)(p - base);
     return w;
 }
@@ -108,23 +120,24 @@ BinWS bin_ws_carve(char* base, int64_t R)
 {
     BinWS w;
     char* p = base;
-    const size_t n = R > 0 ? (size_t)R : 1;
-    w.point_list = carve<uint32_t>(p, n);
-    w.keys = carve<uint64_t>(p, n);
-    w.point_list_unsorted = carve<uint32_t>(p, n);
-    w.keys_unsorted = carve<uint64_t>(p, n);
-    w.sort_temp_bytes = sort_temp_bytes(R);
-    w.sort_temp = carve<char>(p, w.sort_temp_bytes);
+    w.point_list = carve<uint32_t>(p, R > 0 ? (size_t)R : 1);
     w.total = (size_t)(p - base);
     return w;
 }
 
-// Smallest b with (n >> b) == 0, as the reference's getHigherMsb (CR/rasterizer_impl.cu:35-50).
-static int bits_for(uint32_t n)
+// Pinned 4-byte slot + event per host thread for the one device->host hand-off of R.
+struct HostSlot {
+    int32_t* pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+static HostSlot& host_slot()
 {
-    int b = 0;
-    while (b < 32 && (n >> b)) b++;
-    return b;
+    static thread_local HostSlot s;
+    if (!s.pinned) {
+        if (cudaHostAlloc((void**)&s.pinned, 64, cudaHostAllocDefault) != cudaSuccess) s.pinned = nullptr;
+        if (cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) != cudaSuccess) s.ev = nullptr;
+    }
+    return s;
 }
 
 static int check_common(const gsr_gaussians* g, const gsr_camera* cam)
@@ -180,17 +193,17 @@ int gsr_profile_collect(float* ms, int* counts)
 }
 const char* gsr_last_error(void) { return g_err.c_str(); }
 
-size_t gsr_geom_ws_bytes(int32_t P) { return geom_ws_carve(nullptr, P).total; }
+size_t gsr_geom_ws_bytes(int32_t P, int32_t W, int32_t H) { return geom_ws_carve(nullptr, P, W, H).total; }
 size_t gsr_img_ws_bytes(int32_t W, int32_t H) { return img_ws_carve(nullptr, W, H).total; }
 size_t gsr_binning_ws_bytes(int64_t R) { return bin_ws_carve(nullptr, R).total; }
 
-void gsr_geom_layout_of(int32_t P, gsr_geom_layout* o)
+void gsr_geom_layout_of(int32_t P, int32_t W, int32_t H, gsr_geom_layout* o)
 {
-    GeomWS w = geom_ws_carve(nullptr, P);
+    GeomWS w = geom_ws_carve(nullptr, P, W, H);
     o->rec = (size_t)w.rec;
-    o->tiles_touched = (size_t)w.tiles_touched;
-    o->point_offsets = (size_t)w.point_offsets;
-    o->scan_temp = (size_t)w.scan_temp;
+    o->rects = (size_t)w.rects;
+    o->depth_keys = (size_t)w.depth_keys;
+    o->sorted_ids = (size_t)w.sort.vals_a;
     o->total = w.total;
 }
 void gsr_img_layout_of(int32_t W, int32_t H, gsr_img_layout* o)
@@ -205,10 +218,6 @@ void gsr_binning_layout_of(int64_t R, gsr_binning_layout* o)
 {
     BinWS w = bin_ws_carve(nullptr, R);
     o->point_list = (size_t)w.point_list;
-    o->keys = (size_t)w.keys;
-    o->point_list_unsorted = (size_t)w.point_list_unsorted;
-    o->keys_unsorted = (size_t)w.keys_unsorted;
-    o->sort_temp = (size_t)w.sort_temp;
     o->total = w.total;
 }
 
@@ -222,9 +231,11 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     if (num_rendered) *num_rendered = 0;
     if (P == 0) return GSR_OK;
     if (!radii || !geom_ws || !img_ws) return fail(GSR_ERR_INVALID, "radii / workspaces required");
-    if (geom_ws_bytes < gsr_geom_ws_bytes(P) || img_ws_bytes < gsr_img_ws_bytes(W, H))
+    if (geom_ws_bytes < gsr_geom_ws_bytes(P, W, H) || img_ws_bytes < gsr_img_ws_bytes(W, H))
         return fail(GSR_ERR_WORKSPACE, "geometry / image workspace too small");
-    GeomWS gw = geom_ws_carve((char*)geom_ws, P);
+    if ((W + kTile - 1) / kTile > 1023 || (H + kTile - 1) / kTile > 1023)
+        return fail(GSR_ERR_INVALID, "image larger than 16368 pixels in one dimension");
+    GeomWS gw = geom_ws_carve((char*)geom_ws, P, W, H);
 
     PreArgs a;
     a.P = P; a.D = g->sh_degree; a.M = g->shs ? g->sh_coeffs : 0; a.W = W; a.H = H;
@@ -235,20 +246,33 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     a.scale_mod = g->scale_modifier; a.tanfovx = cam->tanfovx; a.tanfovy = cam->tanfovy;
     a.focal_y = H / (2.0f * cam->tanfovy);
     a.focal_x = W / (2.0f * cam->tanfovx);
-    a.radii = radii; a.rec = gw.rec; a.tiles = gw.tiles_touched;
+    a.radii = radii; a.rec = gw.rec; a.rects = gw.rects; a.depth_keys = gw.depth_keys; a.num_rendered = gw.counters;
     prof_mark(ST_BEGIN, stream);
+    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, sizeof(uint32_t), stream));
     launch_preprocess_fwd(a, stream);
     GSR_STAGE("preprocess", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS, stream, 1);
-    launch_scan(gw.tiles_touched, gw.point_offsets, P, gw.scan_temp, gw.scan_temp_bytes, stream);
-    GSR_STAGE("scan", cam->debug, stream);
-    GSR_MARK(ST_SCAN, stream, 0);
-    if (num_rendered) {
+    // R goes to the host through a pinned slot + event, so the depth sort (which does not need R) is
+    // already running while the caller waits for R and allocates the instance list.
+    HostSlot& hs = host_slot();
+    const bool async_r = num_rendered && hs.pinned && hs.ev;
+    if (async_r) {
+        GSR_CUDA(cudaMemcpyAsync(hs.pinned, gw.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GSR_CUDA(cudaEventRecord(hs.ev, stream));
+    }
+    launch_depth_sort(gw.depth_keys, P, gw.sort, stream);
+    GSR_STAGE("depth_sort", cam->debug, stream);
+    GSR_MARK(ST_DEPTH_SORT, stream, 9);
+    if (async_r) {
+        GSR_CUDA(cudaEventSynchronize(hs.ev));
+        *num_rendered = *hs.pinned;
+    } else if (num_rendered) {
         uint32_t r = 0;
-        GSR_CUDA(cudaMemcpyAsync(&r, gw.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GSR_CUDA(cudaMemcpyAsync(&r, gw.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         GSR_CUDA(cudaStreamSynchronize(stream));
         *num_rendered = (int32_t)r;
     }
+    if (num_rendered && *num_rendered < 0) return fail(GSR_ERR_INVALID, "more than 2^31-1 tile instances");
     return GSR_OK;
 }
 
@@ -268,23 +292,16 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     if (!radii || !geom_ws || !img_ws || (R > 0 && !binning_ws))
         return fail(GSR_ERR_INVALID, "radii / workspaces required");
     if (binning_ws_bytes < gsr_binning_ws_bytes(R)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
-    GeomWS gw = geom_ws_carve((char*)geom_ws, P);
+    GeomWS gw = geom_ws_carve((char*)geom_ws, P, W, H);
     ImgWS iw = img_ws_carve((char*)img_ws, W, H);
     BinWS bw = bin_ws_carve((char*)binning_ws, R);
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (R > 0) {
-        launch_duplicate(P, gw.rec, radii, gw.point_offsets, bw.keys_unsorted, bw.point_list_unsorted, gx, gy, stream);
-        GSR_STAGE("duplicate", cam->debug, stream);
-        GSR_MARK(ST_DUPLICATE, stream, 1);
-        launch_sort(bw, R, 32 + bits_for((uint32_t)(gx * gy)), stream);
-        GSR_STAGE("sort", cam->debug, stream);
-        GSR_MARK(ST_SORT, stream, 0);
-    }
-    launch_tile_ranges(R, bw.keys, iw.ranges, gx * gy, stream);
-    GSR_STAGE("tile_ranges", cam->debug, stream);
-    GSR_MARK(ST_RANGES, stream, R > 0 ? 1 : 0);
+    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.point_list, stream) != 0)
+        return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
+    GSR_STAGE("tile_partition", cam->debug, stream);
+    GSR_MARK(ST_TILE_PARTITION, stream, 4);
     launch_render_fwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
                       out_color, stream);
     GSR_STAGE("render", cam->debug, stream);
@@ -306,7 +323,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     const int M = g->shs ? g->sh_coeffs : 0;
     if ((M > 0 && !gr->dL_dsh) || (g->scales && (!gr->dL_dscales || !gr->dL_drotations)))
         return fail(GSR_ERR_INVALID, "gradient buffer for a provided input missing");
-    GeomWS gw = geom_ws_carve((char*)geom_ws, P);
+    GeomWS gw = geom_ws_carve((char*)geom_ws, P, W, H);
     ImgWS iw = img_ws_carve((char*)img_ws, W, H);
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 

@@ -19,12 +19,20 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 //   rec[3i+2] = (r, g, b, bits)                 bits: SH clamp flags (bit ch set => channel clamped)
 // The reference keeps these in separate arrays (GeometryState, CR/rasterizer_impl.h:29-44) and
 // additionally stores cov3D (24 B) which the backward here recomputes from scale/rotation.
+struct SortWS {
+    uint32_t *keys_a, *vals_a, *keys_b, *vals_b;   // depth-sort ping-pong (P each); result in keys_a / vals_a
+    uint32_t* hist;                                // [sort_chunks(P)][2048]
+    uint32_t* totals;                              // [2048]
+    uint32_t* tile_hist;                           // [partition CTAs][T]
+    uint32_t* tile_totals;                         // [T]
+    uint32_t* tile_starts;                         // [T]
+};
 struct GeomWS {
     float4* rec;
-    uint32_t* tiles_touched;
-    uint32_t* point_offsets;
-    char* scan_temp;
-    size_t scan_temp_bytes;
+    ushort4* rects;        // tile rectangle {x0, y0, x1, y1}; empty for culled Gaussians
+    uint32_t* depth_keys;  // float bits of the view depth; 0xFFFFFFFF for culled Gaussians
+    uint32_t* counters;    // [0] = R (number of tile instances)
+    SortWS sort;
     size_t total;
 };
 struct ImgWS {
@@ -35,19 +43,14 @@ struct ImgWS {
 };
 struct BinWS {
     uint32_t* point_list;
-    uint64_t* keys;
-    uint32_t* point_list_unsorted;
-    uint64_t* keys_unsorted;
-    char* sort_temp;
-    size_t sort_temp_bytes;
     size_t total;
 };
 
-GeomWS geom_ws_carve(char* base, int P);
+GeomWS geom_ws_carve(char* base, int P, int W, int H);
 ImgWS img_ws_carve(char* base, int W, int H);
 BinWS bin_ws_carve(char* base, int64_t R);
-size_t scan_temp_bytes(int P);
-size_t sort_temp_bytes(int64_t R);
+int sort_chunks(int P);
+void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem_count, size_t& smem_scatter);
 
 // ---- launchers (each enqueues on `s`) ---------------------------------------------------------
 struct PreArgs {
@@ -56,17 +59,17 @@ struct PreArgs {
     float scale_mod, tanfovx, tanfovy, focal_x, focal_y;
     int* radii;
     float4* rec;
-    uint32_t* tiles;
+    ushort4* rects;
+    uint32_t* depth_keys;
+    uint32_t* num_rendered;   // device counter, zeroed by the caller
 };
 void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, const float* proj, uint8_t* present,
                          cudaStream_t s);
 
-void launch_scan(const uint32_t* in, uint32_t* out, int P, char* temp, size_t temp_bytes, cudaStream_t s);
-void launch_duplicate(int P, const float4* rec, const int* radii, const uint32_t* offsets, uint64_t* keys,
-                      uint32_t* vals, int gx, int gy, cudaStream_t s);
-void launch_sort(BinWS& b, int64_t R, int end_bit, cudaStream_t s);
-void launch_tile_ranges(int64_t R, const uint64_t* keys, uint2* ranges, int tiles, cudaStream_t s);
+void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s);
+int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
+                          uint32_t* point_list, cudaStream_t s);
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,

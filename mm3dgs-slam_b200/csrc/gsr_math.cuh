@@ -207,6 +207,7 @@ struct PreOut {
     float px, py;    // pixel-space mean
     float cx, cy, cz; // conic (inverse 2-D covariance)
     float lam_max;   // larger eigenvalue of the 2-D covariance (for the blend kernels' cull radius)
+    int x0, y0, x1, y1; // tile rectangle
 };
 
 GSR_HD PreOut preprocess_one(const V3& p, const float* cov6, const float* view, const float* proj, int W, int H,
@@ -217,6 +218,7 @@ GSR_HD PreOut preprocess_one(const V3& p, const float* cov6, const float* view, 
     o.tiles = 0;
     o.depth = 0.f;
     o.px = o.py = o.cx = o.cy = o.cz = o.lam_max = 0.f;
+    o.x0 = o.y0 = o.x1 = o.y1 = 0;
     V4 p_hom = xform4x4(p, proj);
     float p_w = 1.0f / (p_hom.w + 0.0000001f);
     float projx = p_hom.x * p_w, projy = p_hom.y * p_w;
@@ -242,6 +244,7 @@ GSR_HD PreOut preprocess_one(const V3& p, const float* cov6, const float* view, 
     if (n == 0) return o;
     o.radius = (int)my_radius;
     o.tiles = n;
+    o.x0 = x0; o.y0 = y0; o.x1 = x1; o.y1 = y1;
     o.depth = p_view.z;
     o.lam_max = fmaxf(lambda1, lambda2);
     return o;

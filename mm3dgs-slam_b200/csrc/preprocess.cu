@@ -86,12 +86,14 @@ __global__ void __launch_bounds__(kPB) k_preprocess_fwd(PreArgs a)
     __shared__ __align__(16) float s_col[kPB * 3];   // SH (M==1) or precomputed colours
     __shared__ __align__(16) float4 s_rec[kPB * 3];
     __shared__ float s_cam[35];
+    __shared__ uint32_t s_tiles;
 
     const int tid = threadIdx.x;
     const int base = blockIdx.x * kPB;
     const int nb = min(kPB, a.P - base);
     const bool has_sr = (a.cov3D_pre == nullptr);
     const bool sh_path = (a.colors == nullptr);
+    if (tid == 0) s_tiles = 0;
 
     stage_in(a.means + (size_t)base * 3, s_means, nb * 3, tid);
     if (has_sr) {
@@ -160,7 +162,14 @@ __global__ void __launch_bounds__(kPB) k_preprocess_fwd(PreArgs a)
             r2 = make_float4(cr, cg, cb, __int_as_float(bits));
         }
         a.radii[idx] = radius;
-        a.tiles[idx] = (uint32_t)tiles;
+        a.rects[idx] = radius > 0 ? make_ushort4((unsigned short)o.x0, (unsigned short)o.y0, (unsigned short)o.x1,
+                                                 (unsigned short)o.y1)
+                                  : make_ushort4(0, 0, 0, 0);
+        a.depth_keys[idx] = radius > 0 ? __float_as_uint(o.depth) : 0xffffffffu;
+    }
+    {   // R = total number of tile instances: warp reduce, one shared atomic per warp, one global per CTA
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)tiles);
+        if ((tid & 31) == 0 && wsum) atomicAdd(&s_tiles, wsum);
     }
     s_rec[3 * tid + 0] = r0;
     s_rec[3 * tid + 1] = r1;
@@ -168,6 +177,7 @@ __global__ void __launch_bounds__(kPB) k_preprocess_fwd(PreArgs a)
     __syncthreads();
     float4* out = a.rec + (size_t)base * 3;
     for (int i = tid; i < nb * 3; i += kPB) out[i] = s_rec[i];
+    if (tid == 0 && s_tiles) atomicAdd(a.num_rendered, s_tiles);
 }
 
 void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s)

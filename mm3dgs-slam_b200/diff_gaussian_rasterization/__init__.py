@@ -76,7 +76,7 @@ def _load():
     lib.gsr_abi_version.restype = ctypes.c_int
     lib.gsr_last_error.restype = ctypes.c_char_p
     lib.gsr_geom_ws_bytes.restype = sz
-    lib.gsr_geom_ws_bytes.argtypes = [i32]
+    lib.gsr_geom_ws_bytes.argtypes = [i32, i32, i32]
     lib.gsr_img_ws_bytes.restype = sz
     lib.gsr_img_ws_bytes.argtypes = [i32, i32]
     lib.gsr_binning_ws_bytes.restype = sz
@@ -150,7 +150,7 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
         color.zero_()
         e = torch.empty(0, **u8)
         return 0, color, radii, e, e, e
-    geom = torch.empty(_lib.gsr_geom_ws_bytes(P), **u8)
+    geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
     img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
     g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg)
     R = ctypes.c_int32(0)

@@ -100,7 +100,7 @@ def test_intermediate_state_bit_exact(dgr, ref, P, W, H, deg, seed):
     torch.cuda.synchronize()
     assert R == f["num_rendered"]
     assert torch.equal(radii, f["radii"])
-    mg, rg = ws_decode.decode_geom(geom, P), ref.decode_geom(f["geom"], P)
+    mg, rg = ws_decode.decode_geom(geom, P, W, H), ref.decode_geom(f["geom"], P)
     vis = (radii > 0).cpu()
     assert torch.equal(mg["tiles_touched"], rg["tiles_touched"])
     for k in ("means2D", "depths", "conic_opacity", "rgb"):
@@ -108,12 +108,19 @@ def test_intermediate_state_bit_exact(dgr, ref, P, W, H, deg, seed):
         assert torch.equal(a, b) or rel_err(a, b) < 1e-6, (k, rel_err(a, b))
     assert torch.equal(mg["depths"][vis], rg["depths"][vis]), "depth bits feed the sort key"
     assert torch.equal(mg["clamped"][vis], rg["clamped"][vis].bool())
-    mb, rb = ws_decode.decode_binning(binning, R), ref.decode_binning(f["binning"], R)
-    assert torch.equal(mb["keys"], rb["keys"])
-    assert torch.equal(mb["point_list"], rb["point_list"])
     mi, ri = ws_decode.decode_img(img, W, H), ref.decode_img(f["img"], W, H)
     T = mi["ranges"].shape[0]
     assert torch.equal(mi["ranges"], ri["ranges"][:T])
+    mb, rb = ws_decode.decode_binning(binning, R, mg, mi), ref.decode_binning(f["binning"], R)
+    assert torch.equal(mb["point_list"], rb["point_list"])
+    assert torch.equal(mb["keys"], rb["keys"])
+    # depth order of the Gaussians themselves: ascending (depth bits, index), culled last
+    sid = mg["sorted_ids"]
+    k = mg["depth_keys"][sid]
+    assert bool((k[1:] >= k[:-1]).all())
+    tie = k[1:] == k[:-1]
+    assert bool((sid[1:][tie] > sid[:-1][tie]).all())
+    assert torch.equal(torch.sort(sid).values, torch.arange(P))
     assert torch.equal(mi["n_contrib"], ri["n_contrib"])
     assert rel_err(mi["final_T"], ri["final_T"]) < 1e-6
     assert rel_err(color, f["color"]) < TOL

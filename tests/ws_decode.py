@@ -8,7 +8,7 @@ import diff_gaussian_rasterization as dgr
 
 
 class _GeomLayout(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "tiles_touched", "point_offsets", "scan_temp", "total")]
+    _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "rects", "depth_keys", "sorted_ids", "total")]
 
 
 class _ImgLayout(ctypes.Structure):
@@ -16,8 +16,7 @@ class _ImgLayout(ctypes.Structure):
 
 
 class _BinLayout(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_size_t) for n in ("point_list", "keys", "point_list_unsorted", "keys_unsorted",
-                                              "sort_temp", "total")]
+    _fields_ = [(n, ctypes.c_size_t) for n in ("point_list", "total")]
 
 
 def _arr(buf, off, dt, count):
@@ -28,16 +27,18 @@ def _arr(buf, off, dt, count):
     return torch.from_numpy(a)
 
 
-def decode_geom(geom, P):
+def decode_geom(geom, P, W, H):
     lay = _GeomLayout()
-    dgr._lib.gsr_geom_layout_of(ctypes.c_int32(P), ctypes.byref(lay))
+    dgr._lib.gsr_geom_layout_of(ctypes.c_int32(P), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(lay))
     rec = _arr(geom, lay.rec, np.float32, 12 * P).view(P, 12)
     bits = rec[:, 11].contiguous().view(torch.int32)
+    rects = _arr(geom, lay.rects, np.uint16, 4 * P).view(P, 4)
     return dict(means2D=rec[:, 0:2].contiguous(), depths=rec[:, 2].contiguous(), cull_r2=rec[:, 3].contiguous(),
                 conic_opacity=rec[:, 4:8].contiguous(), rgb=rec[:, 8:11].contiguous(),
                 clamped=torch.stack([(bits & 1) != 0, (bits & 2) != 0, (bits & 4) != 0], -1),
-                tiles_touched=_arr(geom, lay.tiles_touched, np.uint32, P),
-                point_offsets=_arr(geom, lay.point_offsets, np.uint32, P))
+                rects=rects, tiles_touched=(rects[:, 2] - rects[:, 0]) * (rects[:, 3] - rects[:, 1]),
+                depth_keys=_arr(geom, lay.depth_keys, np.uint32, P),
+                sorted_ids=_arr(geom, lay.sorted_ids, np.uint32, P))
 
 
 def decode_img(img, W, H):
@@ -49,7 +50,15 @@ def decode_img(img, W, H):
                 ranges=_arr(img, lay.ranges, np.uint32, 2 * T).view(T, 2))
 
 
-def decode_binning(binning, R):
+def decode_binning(binning, R, geom_dec, img_dec):
+    """point_list plus the (tile << 32 | depth bits) key of every instance, reconstructed from the tile
+    ranges and the per-Gaussian depth keys (the library never materialises 64-bit keys)."""
     lay = _BinLayout()
     dgr._lib.gsr_binning_layout_of(ctypes.c_int64(R), ctypes.byref(lay))
-    return dict(point_list=_arr(binning, lay.point_list, np.uint32, R), keys=_arr(binning, lay.keys, np.uint64, R))
+    pl = _arr(binning, lay.point_list, np.uint32, R)
+    rng = img_dec["ranges"]
+    tile_of = torch.zeros(R, dtype=torch.int64)
+    for t in torch.nonzero(rng[:, 1] > rng[:, 0]).reshape(-1).tolist():
+        tile_of[int(rng[t, 0]):int(rng[t, 1])] = t
+    keys = (tile_of << 32) | geom_dec["depth_keys"][pl]
+    return dict(point_list=pl, keys=keys)
