@@ -45,23 +45,29 @@ def _run(cmd, verbose):
         raise RuntimeError("nvcc failed")
 
 
-def build(force=False, verbose=False, ptxas_info=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, ptxas_info=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=["GSR_TILE_MATCH_HW=1"], out=".../libvariant.so")."""
+    global SO
+    if out is None and not force and not needs_build():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" if out is None else "obj_" + os.path.basename(out))
+    so = SO if out is None else out
     os.makedirs(objdir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if ptxas_info else []
     jobs, objs = [], []
     for s in SOURCES:
         o = os.path.join(objdir, s + ".o")
         objs.append(o)
-        jobs.append([NVCC, "-c", os.path.join(CSRC, s), "-o", o] + ARCH + CFLAGS + extra)
+        jobs.append([NVCC, "-c", os.path.join(CSRC, s), "-o", o] + ARCH + CFLAGS + extra + ["-D" + d for d in defines])
     with ThreadPoolExecutor(len(jobs)) as ex:
         list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))
-    _run([NVCC, "-shared", "-o", SO] + objs + ARCH + ["-cudart", "shared", "-Xcompiler", "-fPIC"], verbose)
-    return SO
+    _run([NVCC, "-shared", "-o", so] + objs + ARCH + ["-cudart", "shared", "-Xcompiler", "-fPIC"], verbose)
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_info="--ptxas" in sys.argv))
+    defs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--define=")]
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_info="--ptxas" in sys.argv,
+                defines=defs, out=outs[0] if outs else None))

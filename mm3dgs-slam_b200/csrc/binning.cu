@@ -29,9 +29,12 @@ namespace gsr {
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;       // 2048
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 16;               // keys per thread
+#ifndef GSR_SORT_ITEMS
+#define GSR_SORT_ITEMS 8
+#endif
+constexpr int kSortItems = GSR_SORT_ITEMS;   // keys per thread
 constexpr int kSortChunk = kSortThreads * kSortItems;   // 4096 keys per CTA
 
 int sort_chunks(int P) { return (P + kSortChunk - 1) / kSortChunk; }
@@ -41,6 +44,21 @@ __device__ __forceinline__ unsigned lanemask_lt()
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// Lanes holding the same `nbits`-bit value as this lane (among lanes with valid == true), built from
+// one ballot per bit (VOTE is cheap; the hardware MATCH.ANY serialises over the distinct values,
+// and the values here — 11-bit digits of random keys, tile ids of neighbouring splats — are
+// almost all distinct within a warp).
+__device__ __forceinline__ unsigned match_any_bits(uint32_t v, bool valid, int nbits)
+{
+    unsigned peers = __ballot_sync(kFullMask, valid);
+    for (int bit = 0; bit < nbits; bit++) {
+        const bool set = (v >> bit) & 1u;
+        const unsigned b = __ballot_sync(kFullMask, set);
+        peers &= set ? b : ~b;
+    }
+    return valid ? peers : 0u;
 }
 
 // Exclusive scan of `n` u32 values in shared memory (n a multiple of blockDim.x, in place), all threads call.
@@ -97,14 +115,15 @@ __global__ void __launch_bounds__(kSortThreads) k_digit_count(const uint32_t* __
 }
 
 // Column scan of H[chunks][bins]: in place H[c][b] <- sum_{c' < c} H[c'][b]; totals[b] <- sum_c H[c][b].
-// One CTA per 32 bins; the chunk axis is split into 8 segments handled by the 8 warps.
-__global__ void __launch_bounds__(256) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
-                                                     uint32_t* __restrict__ totals)
+// One CTA per 32 bins; the chunk axis is split into 32 segments handled by the 32 warps.
+constexpr int kScanSegs = 32;
+__global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
+                                                                uint32_t* __restrict__ totals)
 {
-    __shared__ uint32_t s_seg[8][32];
+    __shared__ uint32_t s_seg[kScanSegs][32];
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
-    const int per = (chunks + 7) / 8;
+    const int per = (chunks + kScanSegs - 1) / kScanSegs;
     const int c0 = min(seg * per, chunks), c1 = min(c0 + per, chunks);
     uint32_t sum = 0;
     if (b < bins)
@@ -120,7 +139,7 @@ __global__ void __launch_bounds__(256) k_column_scan(uint32_t* __restrict__ hist
             hist[o] = run;
             run += v;
         }
-        if (seg == 7) totals[b] = run;
+        if (seg == kScanSegs - 1) totals[b] = run;
     }
 }
 
@@ -132,13 +151,14 @@ __global__ void __launch_bounds__(kSortThreads) k_digit_scatter(const uint32_t* 
                                                                 uint32_t* __restrict__ keys_out,
                                                                 uint32_t* __restrict__ vals_out)
 {
-    __shared__ uint32_t s_start[kBins];               // absolute start of this CTA's run, per bin
-    __shared__ uint16_t s_cnt[kSortWarps][kBins];     // per-warp counters / running offsets
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* s_start = s_dyn;                                                    // [kBins] absolute start of this CTA's run
+    uint16_t (*s_cnt)[kBins] = reinterpret_cast<uint16_t (*)[kBins]>(s_dyn + kBins);  // [kSortWarps][kBins] per-warp counters
     __shared__ uint32_t s_scan[kSortWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int b = tid; b < kBins; b += kSortThreads) s_start[b] = totals[b];
-    for (int i = tid; i < kSortWarps * kBins / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(&s_cnt[0][0])[i] = 0;
+    for (int i = tid; i < kSortWarps * kBins / 2; i += kSortThreads) (s_dyn + kBins)[i] = 0;
     __syncthreads();
     block_exclusive_scan<kBins / kSortThreads>(s_start, s_scan);    // bin starts over the whole array
     const uint32_t* row = base + (size_t)blockIdx.x * kBins;
@@ -159,7 +179,7 @@ __global__ void __launch_bounds__(kSortThreads) k_digit_scatter(const uint32_t* 
         const int i = wbase + j * 32 + lane;
         const bool valid = i < n;
         const uint32_t d = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(kFullMask, d);
+        const unsigned peers = __match_any_sync(kFullMask, d);   // digits of random keys: hardware MATCH measured faster
         if (valid && (peers & lanemask_lt()) == 0) s_cnt[warp][d] += (uint16_t)__popc(peers);
         __syncwarp();
     }
@@ -208,10 +228,12 @@ void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_
     uint32_t* vout[3] = {w.vals_a, w.vals_b, w.vals_a};
     const int shifts[3] = {0, 11, 22};
     const uint32_t masks[3] = {2047u, 2047u, 1023u};
+    const size_t smem = (size_t)kBins * 4 + (size_t)kSortWarps * kBins * 2;
+    cudaFuncSetAttribute(k_digit_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int p = 0; p < 3; p++) {
         k_digit_count<<<C, kSortThreads, 0, s>>>(kin, P, shifts[p], masks[p], w.hist);
-        k_column_scan<<<kBins / 32, 256, 0, s>>>(w.hist, C, kBins, w.totals);
-        k_digit_scatter<<<C, kSortThreads, 0, s>>>(kin, vin, P, shifts[p], masks[p], w.hist, w.totals, kout[p], vout[p]);
+        k_column_scan<<<kBins / 32, 32 * kScanSegs, 0, s>>>(w.hist, C, kBins, w.totals);
+        k_digit_scatter<<<C, kSortThreads, smem, s>>>(kin, vin, P, shifts[p], masks[p], w.hist, w.totals, kout[p], vout[p]);
         kin = kout[p];
         vin = vout[p];
     }
@@ -221,9 +243,12 @@ void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_
 // ================================================================================================
 // 2. Tile partition (R instances, generated on the fly from the depth-ordered Gaussians)
 // ================================================================================================
-// Walks `cnt` flattened instances of the 32 Gaussians held by the lanes of a warp (lane l owns a
-// rect of n_l = w_l*h_l tiles), 32 instances per step in lane-major order, and calls f(tile, src_lane)
-// on each valid instance.  `packed` = x0 | y0 << 10 | w << 20 per lane (x0,y0 < 1024, w < 4096).
+// Walks the flattened instances of the 32 Gaussians held by the lanes of a warp (lane l owns a rect
+// of n_l = w_l*h_l tiles), 32 instances per step in lane-major order, and calls f(tile, src_lane, valid)
+// for every lane in every step.  `packed` = x0 | y0 << 10 | w << 20 per lane (x0,y0 < 1024, w < 4096).
+// Non-empty lanes must precede empty ones (true for depth-sorted Gaussians: culled ones sort last),
+// so the exclusive offsets of the non-empty lanes are strictly increasing and the source lane of
+// instance i is found with one __reduce_or_sync + popc instead of a shuffle binary search.
 template <typename F>
 __device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t n_l, int gx, F&& f)
 {
@@ -235,28 +260,29 @@ __device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t
         if (lane >= o) incl += t;
     }
     const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+    const uint32_t excl = incl - n_l;
+    // exact k / w for k*w < 2^32 (k < 2^20 instances per splat, w < 2^12): q = umulhi(k, ceil(2^32 / w))
+    const uint32_t magic = 0xffffffffu / (packed >> 20) + 1u;
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
     for (uint32_t b = 0; b < total; b += 32) {
         const uint32_t i = b + lane;
         const bool valid = i < total;
-        // source lane = number of lanes whose inclusive count is <= i
-        int src = 0;
-#pragma unroll
-        for (int stepw = 16; stepw > 0; stepw >>= 1) {
-            const uint32_t probe = __shfl_sync(kFullMask, incl, src + stepw - 1);
-            if (probe <= i) src += stepw;
-        }
-        src = min(src, 31);
-        const uint32_t s_incl = __shfl_sync(kFullMask, incl, src);
-        const uint32_t s_n = __shfl_sync(kFullMask, n_l, src);
+        // lanes whose run starts inside this window mark their start; lanes that started before count as base
+        const unsigned started_before = __ballot_sync(kFullMask, n_l != 0 && excl < b);
+        const unsigned starts = __reduce_or_sync(kFullMask, (n_l != 0 && (excl - b) < 32u) ? (1u << (excl - b)) : 0u);
+        const int src = max(__popc(started_before) + __popc(starts & le_mask) - 1, 0);
+        const uint32_t s_excl = __shfl_sync(kFullMask, excl, src);
         const uint32_t s_pk = __shfl_sync(kFullMask, packed, src);
+        const uint32_t s_magic = __shfl_sync(kFullMask, magic, src);
         uint32_t tile = 0xffffffffu;
         if (valid) {
-            const uint32_t k = i - (s_incl - s_n);
+            const uint32_t k = i - s_excl;
             const uint32_t w = s_pk >> 20, x0 = s_pk & 1023u, y0 = (s_pk >> 10) & 1023u;
-            const uint32_t ry = k / w, rx = k - ry * w;
+            const uint32_t ry = (w == 1u) ? k : __umulhi(k, s_magic);
+            const uint32_t rx = k - ry * w;
             tile = (y0 + ry) * (uint32_t)gx + x0 + rx;
         }
-        f(tile, src, valid);
+        f(tile, src, valid, i);
     }
 }
 
@@ -275,10 +301,15 @@ __device__ __forceinline__ void load_rect(const uint32_t* __restrict__ perm, con
     }
 }
 
-// Dynamic shared memory: uint32 s_hist[T].
-__global__ void __launch_bounds__(256) k_tile_count(const uint32_t* __restrict__ perm, int n, int per_cta,
+// Pass A.  Every warp owns a contiguous range of depth-ordered Gaussians.  It (1) sums its instance
+// count and claims a contiguous segment of the instance stream with one atomicAdd (segments of
+// different warps may sit anywhere in the stream; only their contents are ordered), (2) enumerates its
+// instances ONCE, writing {tile, Gaussian id} records with coalesced 8-byte stores, and (3) adds them to
+// the CTA's tile histogram (row c of H).  Dynamic shared memory: uint32 s_hist[T].
+__global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict__ perm, int n, int per_cta,
                                                     const ushort4* __restrict__ rects, int gx, int T,
-                                                    uint32_t* __restrict__ hist)
+                                                    uint32_t* __restrict__ hist, uint2* __restrict__ stream,
+                                                    uint2* __restrict__ segs, uint32_t* __restrict__ claim)
 {
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_hist = s_dyn;
@@ -288,12 +319,32 @@ __global__ void __launch_bounds__(256) k_tile_count(const uint32_t* __restrict__
     const int c0 = blockIdx.x * per_cta, c1 = min(c0 + per_cta, n);
     const int per_warp = (per_cta + nwarps - 1) / nwarps;
     const int w0 = c0 + warp * per_warp, w1 = min(w0 + per_warp, c1);
+    uint32_t mine = 0;
     for (int g0 = w0; g0 < w1; g0 += 32) {
         uint32_t id, packed, cnt;
         load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
-        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int, bool valid) {
-            if (valid) atomicAdd(&s_hist[tile], 1u);
+        mine += cnt;
+    }
+    const uint32_t wtotal = __reduce_add_sync(kFullMask, mine);
+    uint32_t seg = 0;
+    if (lane == 0) {
+        seg = wtotal ? atomicAdd(claim, wtotal) : 0u;
+        segs[(size_t)blockIdx.x * nwarps + warp] = make_uint2(seg, wtotal);
+    }
+    seg = __shfl_sync(kFullMask, seg, 0);
+    uint32_t done = 0;
+    for (int g0 = w0; g0 < w1; g0 += 32) {
+        uint32_t id, packed, cnt;
+        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
+        const uint32_t round_total = __reduce_add_sync(kFullMask, cnt);
+        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int src, bool valid, uint32_t i) {
+            const uint32_t gid = __shfl_sync(kFullMask, id, src);
+            if (valid) {
+                stream[(size_t)seg + done + i] = make_uint2(tile, gid);
+                atomicAdd(&s_hist[tile], 1u);
+            }
         });
+        done += round_total;
     }
     __syncthreads();
     uint32_t* row = hist + (size_t)blockIdx.x * T;
@@ -334,12 +385,28 @@ __global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict
     }
 }
 
+#ifndef GSR_TILE_MATCH_HW
+#define GSR_TILE_MATCH_HW 0
+#endif
+__device__ __forceinline__ unsigned tile_peers(uint32_t tile, bool valid, int tbits)
+{
+#if GSR_TILE_MATCH_HW
+    return __match_any_sync(kFullMask, valid ? tile : 0xffffffffu);
+#else
+    return match_any_bits(tile, valid, tbits);
+#endif
+}
+
+// Pass B.  Same CTA / warp <-> Gaussian-range mapping as pass A; no enumeration any more: each warp
+// streams its segment twice with coalesced 8-byte accesses.
+//   sweep 1: rank every instance inside the warp's range for its tile (per-warp 16-bit counters,
+//            same-tile lanes of a step ranked in lane order) and store the rank back into the record;
+//   prefix : per tile, exclusive prefix of the warp counts over the CTA's warps (+ CTA base + tile start);
+//   sweep 2: point_list[start[tile] + prefix[warp][tile] + rank] = Gaussian id.
 // Dynamic shared memory: uint32 s_start[T]; uint16 s_cnt[nwarps][T].
-__global__ void __launch_bounds__(256) k_tile_scatter(const uint32_t* __restrict__ perm, int n, int per_cta,
-                                                      const ushort4* __restrict__ rects, int gx, int T,
-                                                      const uint32_t* __restrict__ base,
-                                                      const uint32_t* __restrict__ starts,
-                                                      uint32_t* __restrict__ point_list)
+__global__ void __launch_bounds__(1024) k_tile_scatter(int T, const uint32_t* __restrict__ base,
+                                                      const uint32_t* __restrict__ starts, uint2* __restrict__ stream,
+                                                      const uint2* __restrict__ segs, uint32_t* __restrict__ point_list)
 {
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_start = s_dyn;
@@ -349,19 +416,38 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const uint32_t* __restrict
     for (int t = tid; t < T; t += blockDim.x) s_start[t] = starts[t] + row[t];
     for (int i = tid; i < nwarps * T; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
-    const int c0 = blockIdx.x * per_cta, c1 = min(c0 + per_cta, n);
-    const int per_warp = (per_cta + nwarps - 1) / nwarps;
-    const int w0 = c0 + warp * per_warp, w1 = min(w0 + per_warp, c1);
+    const uint2 seg = segs[(size_t)blockIdx.x * nwarps + warp];
+    uint2* my_stream = stream + seg.x;
+    const uint32_t len = seg.y;
     uint16_t* my = s_cnt + (size_t)warp * T;
-    // counting sweep
-    for (int g0 = w0; g0 < w1; g0 += 32) {
-        uint32_t id, packed, cnt;
-        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
-        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int, bool valid) {
-            const unsigned peers = __match_any_sync(kFullMask, tile);
-            if (valid && (peers & lanemask_lt()) == 0) my[tile] += (uint16_t)__popc(peers);
+    int tbits = 1;
+    while ((1 << tbits) < T) tbits++;
+    // sweep 1 (records are loaded four steps ahead: the per-step work is a short dependent chain, so
+    // an un-prefetched L2 round trip per step would dominate the warps that own a very large splat)
+    for (uint32_t b0 = 0; b0 < len; b0 += 128) {
+        uint32_t tl[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = b0 + u * 32 + lane;
+            tl[u] = (i < len) ? my_stream[i].x : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = b0 + u * 32 + lane;
+            if (b0 + u * 32 >= len) break;
+            const bool valid = i < len;
+            const uint32_t tile = tl[u];
+            const unsigned peers = tile_peers(tile, valid, tbits);
+            const int leader = valid ? __ffs(peers) - 1 : lane;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = my[tile];
+                my[tile] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(kFullMask, old, leader);
+            if (valid) my_stream[i].x = tile | ((old + __popc(peers & lanemask_lt())) << 16);
             __syncwarp();
-        });
+        }
     }
     __syncthreads();
     for (int t = tid; t < T; t += blockDim.x) {
@@ -373,23 +459,22 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const uint32_t* __restrict
         }
     }
     __syncthreads();
-    // ranking sweep
-    for (int g0 = w0; g0 < w1; g0 += 32) {
-        uint32_t id, packed, cnt;
-        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
-        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int src, bool valid) {
-            const unsigned peers = __match_any_sync(kFullMask, tile);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (valid && lane == leader) {
-                old = my[tile];
-                my[tile] = (uint16_t)(old + __popc(peers));
+    // sweep 2
+    for (uint32_t b0 = 0; b0 < len; b0 += 128) {
+        uint2 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = b0 + u * 32 + lane;
+            r[u] = (i < len) ? my_stream[i] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = b0 + u * 32 + lane;
+            if (i < len) {
+                const uint32_t tile = r[u].x & 0xffffu, rank = r[u].x >> 16;
+                point_list[s_start[tile] + my[tile] + rank] = r[u].y;
             }
-            old = __shfl_sync(kFullMask, old, leader);
-            const uint32_t gid = __shfl_sync(kFullMask, id, src);
-            if (valid) point_list[s_start[tile] + old + __popc(peers & lanemask_lt())] = gid;
-            __syncwarp();
-        });
+        }
     }
 }
 
@@ -397,34 +482,47 @@ __global__ void __launch_bounds__(256) k_tile_scatter(const uint32_t* __restrict
 // Gaussians; the CTA count is capped so that the H matrix stays small.
 void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem_count, size_t& smem_scatter)
 {
-    warps = 8;
+    // as many warps per CTA as the 16-bit per-warp counters allow in 200 KB of shared memory, at most 32:
+    // the kernels are latency-bound walks, so short per-warp ranges matter more than anything else.
+    warps = 32;
     while (warps > 1 && (size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024) warps >>= 1;
+    if ((size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
+#ifdef GSR_PLAN_SINGLE_WAVE
+    // one resident wave: CTAs per SM limited by shared memory and by 2048 threads
+    const size_t smem1 = (size_t)T * (4 + 2 * (size_t)(warps > 0 ? warps : 1));
+    int per_sm = (int)((220 * 1024) / (smem1 ? smem1 : 1));
+    per_sm = per_sm < 1 ? 1 : per_sm;
+    if (per_sm * warps * 32 > 2048) per_sm = 2048 / (warps * 32 > 0 ? warps * 32 : 32);
+    const int max_ctas = 148 * (per_sm < 1 ? 1 : per_sm);
+#else
     const int max_ctas = 4 * 148;
-    per_cta = 2048;
+#endif
+    per_cta = 64 * (warps > 0 ? warps : 1);
+    if (per_cta < 1024) per_cta = 1024;
     if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
     per_cta = (per_cta + 31) / 32 * 32;
     ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
     smem_count = (size_t)T * 4;
-    smem_scatter = (size_t)T * (4 + 2 * (size_t)warps);
+    smem_scatter = (size_t)T * (4 + 2 * (size_t)(warps > 0 ? warps : 1));
 }
 
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint32_t* point_list, cudaStream_t s)
+                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;
     int ctas, per_cta, warps;
     size_t smem_c, smem_s;
     tile_partition_plan(P, T, ctas, per_cta, warps, smem_c, smem_s);
-    if (smem_s > 220 * 1024 || per_cta / warps > 65535) return -1;   // image / scene too large for this scheme
+    if (warps == 0 || smem_s > 220 * 1024 || per_cta / warps > 65535) return -1;   // image / scene too large for this scheme
     if (smem_s > 48 * 1024) {   // opt in to the large B200 carve-out (per device, cheap host call)
         cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
-    k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist);
-    k_column_scan<<<(T + 31) / 32, 256, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals);
+    cudaMemsetAsync(claim, 0, sizeof(uint32_t), s);
+    k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, claim);
+    k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals);
     k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts);
-    k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist, w.tile_starts,
-                                                    point_list);
+    k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list);
     return 0;
 }
 

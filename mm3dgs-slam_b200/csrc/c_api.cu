@@ -99,6 +99,7 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.sort.tile_hist = carve<uint32_t>(p, (size_t)ctas * T);
     w.sort.tile_totals = carve<uint32_t>(p, (size_t)T);
     w.sort.tile_starts = carve<uint32_t>(p, (size_t)T);
+    w.sort.segs = carve<uint2>(p, (size_t)ctas * 32);
     w.total = (size_t)(p - base);
     return w;
 }
@@ -121,6 +122,7 @@ BinWS bin_ws_carve(char* base, int64_t R)
     BinWS w;
     char* p = base;
     w.point_list = carve<uint32_t>(p, R > 0 ? (size_t)R : 1);
+    w.stream = carve<uint2>(p, R > 0 ? (size_t)R : 1);
     w.total = (size_t)(p - base);
     return w;
 }
@@ -298,7 +300,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.point_list, stream) != 0)
+    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters + 1, bw.point_list, stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 4);

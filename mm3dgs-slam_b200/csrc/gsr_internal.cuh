@@ -26,6 +26,7 @@ struct SortWS {
     uint32_t* tile_hist;                           // [partition CTAs][T]
     uint32_t* tile_totals;                         // [T]
     uint32_t* tile_starts;                         // [T]
+    uint2* segs;                                   // [partition CTAs * warps] {stream offset, length}
 };
 struct GeomWS {
     float4* rec;
@@ -42,7 +43,8 @@ struct ImgWS {
     size_t total;
 };
 struct BinWS {
-    uint32_t* point_list;
+    uint32_t* point_list;   // [R] final per-tile, depth-ordered Gaussian ids
+    uint2* stream;          // [R] {tile | rank << 16, Gaussian id} in enumeration order (scratch of the partition)
     size_t total;
 };
 
@@ -69,7 +71,7 @@ void launch_mark_visible(int P, const float* means, const float* view, const flo
 
 void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s);
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint32_t* point_list, cudaStream_t s);
+                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s);
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
