@@ -249,8 +249,9 @@ void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_
 // Non-empty lanes must precede empty ones (true for depth-sorted Gaussians: culled ones sort last),
 // so the exclusive offsets of the non-empty lanes are strictly increasing and the source lane of
 // instance i is found with one __reduce_or_sync + popc instead of a shuffle binary search.
+// `kb` = index of the lane's first instance inside its splat (a warp's range may start mid-splat).
 template <typename F>
-__device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t n_l, int gx, F&& f)
+__device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t kb, uint32_t n_l, int gx, F&& f)
 {
     const int lane = threadIdx.x & 31;
     uint32_t incl = n_l;
@@ -271,7 +272,7 @@ __device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t
         const unsigned started_before = __ballot_sync(kFullMask, n_l != 0 && excl < b);
         const unsigned starts = __reduce_or_sync(kFullMask, (n_l != 0 && (excl - b) < 32u) ? (1u << (excl - b)) : 0u);
         const int src = max(__popc(started_before) + __popc(starts & le_mask) - 1, 0);
-        const uint32_t s_excl = __shfl_sync(kFullMask, excl, src);
+        const uint32_t s_excl = __shfl_sync(kFullMask, excl - kb, src);   // (i - s_excl) = index inside the splat
         const uint32_t s_pk = __shfl_sync(kFullMask, packed, src);
         const uint32_t s_magic = __shfl_sync(kFullMask, magic, src);
         uint32_t tile = 0xffffffffu;
@@ -301,11 +302,15 @@ __device__ __forceinline__ void load_rect(const uint32_t* __restrict__ perm, con
     }
 }
 
-// Pass A.  Every warp owns a contiguous range of depth-ordered Gaussians.  It (1) sums its instance
-// count and claims a contiguous segment of the instance stream with one atomicAdd (segments of
-// different warps may sit anywhere in the stream; only their contents are ordered), (2) enumerates its
-// instances ONCE, writing {tile, Gaussian id} records with coalesced 8-byte stores, and (3) adds them to
-// the CTA's tile histogram (row c of H).  Dynamic shared memory: uint32 s_hist[T].
+// Pass A.  A CTA owns a contiguous chunk of depth-ordered Gaussians.  It loads their tile rectangles,
+// scans the instance counts in shared memory and gives every warp an EQUAL share of the chunk's
+// instances (a share may start and end in the middle of a splat — a splat's tiles are distinct, so any
+// cut keeps the per-tile order intact).  Splats covering hundreds of tiles would otherwise serialise
+// the one warp that owns them.  Each warp then (1) claims a contiguous segment of the instance stream
+// with one atomicAdd (segments may sit anywhere in the stream; only their contents are ordered),
+// (2) enumerates its instances ONCE, writing {tile, Gaussian id} records with coalesced 8-byte stores,
+// and (3) adds them to the CTA's tile histogram (row c of H).
+// Dynamic shared memory: uint32 s_hist[T], s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1].
 __global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict__ perm, int n, int per_cta,
                                                     const ushort4* __restrict__ rects, int gx, int T,
                                                     uint32_t* __restrict__ hist, uint2* __restrict__ stream,
@@ -313,38 +318,87 @@ __global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict_
 {
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_hist = s_dyn;
+    uint32_t* s_id = s_dyn + T;
+    uint32_t* s_pk = s_id + per_cta;
+    uint32_t* s_ex = s_pk + per_cta;       // [per_cta + 1] exclusive instance offsets inside the chunk
+    __shared__ uint32_t s_wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (int t = tid; t < T; t += blockDim.x) s_hist[t] = 0;
-    __syncthreads();
-    const int c0 = blockIdx.x * per_cta, c1 = min(c0 + per_cta, n);
-    const int per_warp = (per_cta + nwarps - 1) / nwarps;
-    const int w0 = c0 + warp * per_warp, w1 = min(w0 + per_warp, c1);
-    uint32_t mine = 0;
-    for (int g0 = w0; g0 < w1; g0 += 32) {
-        uint32_t id, packed, cnt;
-        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
-        mine += cnt;
+    const int c0 = blockIdx.x * per_cta;
+    const int m = min(per_cta, n - c0);    // Gaussians in this chunk
+    // load + block-wide exclusive scan of the counts (thread t owns the contiguous slice [t*q, (t+1)*q))
+    const int q = (per_cta + blockDim.x - 1) / blockDim.x;
+    uint32_t run = 0;
+    for (int j = 0; j < q; j++) {
+        const int g = tid * q + j;
+        if (g < per_cta) {
+            uint32_t id, packed, cnt;
+            load_rect(perm, rects, g < m ? c0 + g : n, n, id, packed, cnt);
+            s_id[g] = id;
+            s_pk[g] = packed;
+            s_ex[g] = run;                 // thread-local exclusive offset, fixed up below
+            run += cnt;
+        }
     }
-    const uint32_t wtotal = __reduce_add_sync(kFullMask, mine);
+    uint32_t incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t tbase = incl - run;
+    for (int w = 0; w < warp; w++) tbase += s_wsum[w];
+    uint32_t S = 0;
+    for (int w = 0; w < nwarps; w++) S += s_wsum[w];
+    for (int j = 0; j < q; j++) {
+        const int g = tid * q + j;
+        if (g < per_cta) s_ex[g] += tbase;
+    }
+    if (tid == 0) s_ex[per_cta] = S;
+    __syncthreads();
+
+    // this warp's share [a, b) of the chunk's S instances
+    const uint32_t a = (uint32_t)(((uint64_t)S * warp) / nwarps), b = (uint32_t)(((uint64_t)S * (warp + 1)) / nwarps);
+    const uint32_t len = b - a;
     uint32_t seg = 0;
     if (lane == 0) {
-        seg = wtotal ? atomicAdd(claim, wtotal) : 0u;
-        segs[(size_t)blockIdx.x * nwarps + warp] = make_uint2(seg, wtotal);
+        seg = len ? atomicAdd(claim, len) : 0u;
+        segs[(size_t)blockIdx.x * nwarps + warp] = make_uint2(seg, len);
     }
     seg = __shfl_sync(kFullMask, seg, 0);
-    uint32_t done = 0;
-    for (int g0 = w0; g0 < w1; g0 += 32) {
-        uint32_t id, packed, cnt;
-        load_rect(perm, rects, (g0 + lane < w1) ? g0 + lane : n, n, id, packed, cnt);
-        const uint32_t round_total = __reduce_add_sync(kFullMask, cnt);
-        warp_for_each_instance(packed, cnt, gx, [&](uint32_t tile, int src, bool valid, uint32_t i) {
-            const uint32_t gid = __shfl_sync(kFullMask, id, src);
-            if (valid) {
-                stream[(size_t)seg + done + i] = make_uint2(tile, gid);
-                atomicAdd(&s_hist[tile], 1u);
+    if (len != 0) {
+        // first splat of the share: last g with s_ex[g] <= a  (s_ex is non-decreasing; zero-count splats only at the end)
+        int lo = 0, hi = per_cta;          // invariant: s_ex[lo] <= a < s_ex[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_ex[mid] <= a) lo = mid; else hi = mid;
+        }
+        uint32_t done = 0;
+        for (int g0 = lo; g0 < per_cta && s_ex[g0] < b; g0 += 32) {
+            const int g = g0 + lane;
+            uint32_t id = 0, packed = 1u << 20, kb = 0, cnt = 0;
+            if (g < per_cta) {
+                const uint32_t ex = s_ex[g], full = s_ex[g + 1] - ex;
+                if (ex < b && full != 0) {
+                    kb = a > ex ? a - ex : 0u;
+                    const uint32_t ke = min(full, b - ex);
+                    cnt = ke - kb;
+                    id = s_id[g];
+                    packed = s_pk[g];
+                }
             }
-        });
-        done += round_total;
+            const uint32_t round_total = __reduce_add_sync(kFullMask, cnt);
+            warp_for_each_instance(packed, kb, cnt, gx, [&](uint32_t tile, int src, bool valid, uint32_t i) {
+                const uint32_t gid = __shfl_sync(kFullMask, id, src);
+                if (valid) {
+                    stream[(size_t)seg + done + i] = make_uint2(tile, gid);
+                    atomicAdd(&s_hist[tile], 1u);
+                }
+            });
+            done += round_total;
+        }
     }
     __syncthreads();
     uint32_t* row = hist + (size_t)blockIdx.x * T;
@@ -352,13 +406,17 @@ __global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict_
 }
 
 // Exclusive scan of the per-tile totals -> ranges[t] = {start, end}.  Single CTA, any T.
+// Also emits `order`: the tile ids sorted by descending list length (log2 buckets) so that the blend
+// kernels start their heaviest tiles first and the light ones fill the tail of the launch.
 __global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict__ totals, int T, uint2* __restrict__ ranges,
-                                                      uint32_t* __restrict__ starts)
+                                                      uint32_t* __restrict__ starts, uint32_t* __restrict__ order)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_bucket[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
+    if (tid < 33) s_bucket[tid] = 0;
     __syncthreads();
     for (int t0 = 0; t0 < T; t0 += 1024) {
         const int t = t0 + tid;
@@ -378,11 +436,22 @@ __global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict
         if (t < T) {
             starts[t] = start;
             ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
+            atomicAdd(&s_bucket[32 - __clz(v)], 1u);   // bucket 0: empty, bucket b: 2^(b-1) <= v < 2^b
         }
         __syncthreads();
         if (tid == 1023) s_carry = carry + wb + incl;
         __syncthreads();
     }
+    if (tid == 0) {   // descending buckets -> exclusive starts
+        uint32_t run = 0;
+        for (int b = 32; b >= 0; b--) {
+            const uint32_t c = s_bucket[b];
+            s_bucket[b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += 1024) order[atomicAdd(&s_bucket[32 - __clz(totals[t])], 1u)] = (uint32_t)t;
 }
 
 #ifndef GSR_TILE_MATCH_HW
@@ -502,26 +571,31 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
     if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
     per_cta = (per_cta + 31) / 32 * 32;
     ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
-    smem_count = (size_t)T * 4;
+    // pass A also keeps id / packed rect / offset of every Gaussian of the chunk in shared memory
+    while ((size_t)T * 4 + (size_t)per_cta * 12 + 4 > 200 * 1024 && per_cta > 1024) {
+        per_cta = (per_cta / 2 + 31) / 32 * 32;
+        ctas = (P + per_cta - 1) / per_cta;
+    }
+    smem_count = (size_t)T * 4 + (size_t)per_cta * 12 + 4;
     smem_scatter = (size_t)T * (4 + 2 * (size_t)(warps > 0 ? warps : 1));
 }
 
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s)
+                          uint32_t* order, uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;
     int ctas, per_cta, warps;
     size_t smem_c, smem_s;
     tile_partition_plan(P, T, ctas, per_cta, warps, smem_c, smem_s);
-    if (warps == 0 || smem_s > 220 * 1024 || per_cta / warps > 65535) return -1;   // image / scene too large for this scheme
-    if (smem_s > 48 * 1024) {   // opt in to the large B200 carve-out (per device, cheap host call)
+    if (warps == 0 || smem_s > 220 * 1024 || smem_c > 220 * 1024 || per_cta > 65535) return -1;   // image / scene too large
+    if (smem_s > 48 * 1024 || smem_c > 48 * 1024) {   // opt in to the large B200 carve-out (per device, cheap host call)
         cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
     cudaMemsetAsync(claim, 0, sizeof(uint32_t), s);
     k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, claim);
     k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals);
-    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts);
+    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts, order);
     k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list);
     return 0;
 }

@@ -40,11 +40,13 @@ struct ImgWS {
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
+    uint32_t* order;   // tile ids, heaviest first (launch order of the blend kernels)
     size_t total;
 };
 struct BinWS {
     uint32_t* point_list;   // [R] final per-tile, depth-ordered Gaussian ids
     uint2* stream;          // [R] {tile | rank << 16, Gaussian id} in enumeration order (scratch of the partition)
+    uint8_t* contrib;       // [R] per list entry: which of the tile's 8 warps blended it in the forward
     size_t total;
 };
 
@@ -71,14 +73,14 @@ void launch_mark_visible(int P, const float* means, const float* view, const flo
 
 void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s);
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s);
+                          uint32_t* order, uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s);
 
-void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
-                       cudaStream_t s);
-void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+                       uint8_t* contrib, cudaStream_t s);
+void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
-                       const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
+                       const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
                        float* dL_dopacity, float* dL_dcolors /*[P,3]*/, cudaStream_t s);
 
 struct PreBwdArgs {

@@ -23,6 +23,16 @@
 
 namespace gsr {
 
+#ifndef GSR_FWD_MIN_CTAS
+#define GSR_FWD_MIN_CTAS 8
+#endif
+// Heaviest-tiles-first launch order (k_tile_starts) is available but off by default: on the benchmark
+// scenes, whose tiles carry similar loads, it measured no gain.
+#ifdef GSR_TILE_ORDER
+#define GSR_TILE_OF_BLOCK ((int)order[blockIdx.x])
+#else
+#define GSR_TILE_OF_BLOCK ((int)blockIdx.x)
+#endif
 constexpr int kBatch = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -61,19 +71,21 @@ __device__ __forceinline__ bool subtile_hit(const TileGeom& g, float x, float y,
 // ----------------------------------------------------------------------------------------------
 // Forward
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(256, GSR_FWD_MIN_CTAS) k_render_fwd(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                    const uint32_t* __restrict__ order,
                                                     const uint32_t* __restrict__ point_list,
                                                     const float4* __restrict__ rec, const float* __restrict__ bg,
                                                     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                                                    float* __restrict__ out_color)
+                                                    float* __restrict__ out_color, uint8_t* __restrict__ contrib)
 {
     __shared__ float4 s_r0[kBatch];  // px, py, depth, cull r^2
     __shared__ float4 s_r1[kBatch];  // conic xyz, opacity
     __shared__ float4 s_r2[kBatch];  // rgb, bits
+    __shared__ uint32_t s_mask[2][kBatch / 32][8];   // [buffer][32-entry group][warp]: entries this warp blended
 
-    const int tile = blockIdx.x;
+    const int tile = GSR_TILE_OF_BLOCK;
     const TileGeom g = tile_geom(tile, gx, W, H);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float pixx = (float)g.px, pixy = (float)g.py;
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -84,8 +96,22 @@ __global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const 
     bool done = !g.inside;
     bool warp_done = __all_sync(kFull, done);
 
-    for (int base = 0; base < n; base += kBatch) {
-        if (__syncthreads_and(warp_done)) break;
+    int buf = 0;
+    for (int base = 0;; base += kBatch) {
+        const bool all_done = __syncthreads_and(warp_done);   // also: every warp has finished the previous batch
+        if (base > 0) {
+            // contribution byte of the previous batch's entry t: bit w set <=> warp w blended it for some pixel.
+            // The backward visits exactly these (warp, entry) pairs and nothing else.
+            const int t = threadIdx.x, pbase = base - kBatch;
+            if (pbase + t < n) {
+                const uint32_t* m = s_mask[buf ^ 1][t >> 5];
+                uint32_t byte = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) byte |= ((m[w] >> (t & 31)) & 1u) << w;
+                contrib[range.x + pbase + t] = (uint8_t)byte;
+            }
+        }
+        if (base >= n || all_done) break;
         const int i = base + (int)threadIdx.x;
         if (i < n) {
             const uint32_t id = point_list[range.x + i];
@@ -94,7 +120,10 @@ __global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const 
             s_r1[threadIdx.x] = __ldg(r + 1);
             s_r2[threadIdx.x] = __ldg(r + 2);
         }
+        if (threadIdx.x < 64) s_mask[buf][threadIdx.x >> 3][threadIdx.x & 7] = 0u;
         __syncthreads();
+        const int cur = buf;
+        buf ^= 1;
         if (warp_done) continue;
         const int cnt = min(kBatch, n - base);
         for (int k = 0; k < cnt; k += 32) {
@@ -104,8 +133,10 @@ __global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const 
                 hit = subtile_hit(g, a.x, a.y, a.w);
             }
             unsigned m = __ballot_sync(kFull, hit);
+            unsigned blended = 0u;
             while (m) {
-                const int j = k + __ffs(m) - 1;
+                const int bit = __ffs(m) - 1;
+                const int j = k + bit;
                 m &= m - 1;
                 const float4 a = s_r0[j];
                 const float4 co = s_r1[j];
@@ -125,9 +156,12 @@ __global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const 
                         C2 += c.z * w;
                         T = test_T;
                         last_contributor = (uint32_t)(base + j + 1);
+                        blended |= 1u << bit;
                     }
                 }
             }
+            blended = __reduce_or_sync(kFull, blended);
+            if (lane == 0) s_mask[cur][k >> 5][warp] = blended;
             if (__all_sync(kFull, done)) {
                 warp_done = true;
                 break;
@@ -145,11 +179,12 @@ __global__ void __launch_bounds__(256) k_render_fwd(int W, int H, int gx, const 
     }
 }
 
-void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
-                       cudaStream_t s)
+                       uint8_t* contrib, cudaStream_t s)
 {
-    k_render_fwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, out_color);
+    k_render_fwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib, out_color,
+                                         contrib);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -163,10 +198,12 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                    const uint32_t* __restrict__ order,
                                                     const uint32_t* __restrict__ point_list,
                                                     const float4* __restrict__ rec, const float* __restrict__ bg,
                                                     const float* __restrict__ final_T,
                                                     const uint32_t* __restrict__ n_contrib,
+                                                    const uint8_t* __restrict__ contrib,
                                                     const float* __restrict__ dL_dpix, float* __restrict__ dL_dmean2D,
                                                     float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
                                                     float* __restrict__ dL_dcolors)
@@ -176,10 +213,10 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
     __shared__ float4 s_r2[kBatch];
     __shared__ uint32_t s_id[kBatch];
     __shared__ float s_acc[9][kBatch];   // per staged splat: m2x m2y cx cy cw op cr cg cb
-    __shared__ uint32_t s_touched[kBatch / 32];
+    __shared__ uint8_t s_cb[kBatch];     // forward's contribution byte: bit w <=> warp w blended this entry
     __shared__ uint32_t s_max;
 
-    const int tile = blockIdx.x;
+    const int tile = GSR_TILE_OF_BLOCK;
     const TileGeom g = tile_geom(tile, gx, W, H);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float pixx = (float)g.px, pixy = (float)g.py;
@@ -214,31 +251,31 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
         __syncthreads();
         {
             const int t = threadIdx.x;
+            uint8_t cb = 0;
             if (t < cnt) {
-                const uint32_t id = point_list[range.x + (uint32_t)(hi - 1 - t)];
-                const float4* r = rec + (size_t)id * 3;
-                s_id[t] = id;
-                s_r0[t] = __ldg(r);
-                s_r1[t] = __ldg(r + 1);
-                s_r2[t] = __ldg(r + 2);
+                const uint32_t p = range.x + (uint32_t)(hi - 1 - t);
+                cb = contrib[p];
+                if (cb) {   // entries nobody blended are never visited: skip their gather
+                    const uint32_t id = point_list[p];
+                    const float4* r = rec + (size_t)id * 3;
+                    s_id[t] = id;
+                    s_r0[t] = __ldg(r);
+                    s_r1[t] = __ldg(r + 1);
+                    s_r2[t] = __ldg(r + 2);
+                }
             }
+            s_cb[t] = cb;
 #pragma unroll
             for (int k = 0; k < 9; k++) s_acc[k][t] = 0.f;
-            if (t < kBatch / 32) s_touched[t] = 0u;
         }
         __syncthreads();
         // first slot this warp cares about: position < wmax  <=>  t > hi-1-wmax
         int t0 = hi - (int)wmax;
         if (t0 < 0) t0 = 0;
         for (int k = (t0 & ~31); k < cnt; k += 32) {
-            bool hit = false;
             const int tt = k + lane;
-            if (tt < cnt && tt >= t0) {
-                const float4 a = s_r0[tt];
-                hit = subtile_hit(g, a.x, a.y, a.w);
-            }
+            const bool hit = (tt < cnt) && ((s_cb[tt] >> warp) & 1u);   // this warp blended it in the forward
             unsigned m = __ballot_sync(kFull, hit);
-            unsigned touched = 0u;
             while (m) {
                 const int b = __ffs(m) - 1;
                 const int j = k + b;
@@ -254,7 +291,8 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                 float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
                 if (live) {
                     const float4 c = s_r2[j];
-                    T = T / (1.f - alpha);
+                    const float inv_1ma = __frcp_rn(1.f - alpha);
+                    T = T * inv_1ma;
                     const float dchannel_dcolor = alpha * T;
                     float dL_dalpha = 0.0f;
                     acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
@@ -271,7 +309,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     v8 = dchannel_dcolor * dLp2;
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                    dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
                     const float dL_dG = co.w * dL_dalpha;
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * co.x - gdy * co.y;
@@ -283,7 +321,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     v4 = -0.5f * gdy * dy * dL_dG;
                     v5 = G * dL_dalpha;
                 }
-                if (__any_sync(kFull, live)) {
+                {   // every visited (warp, entry) pair has a live lane (forward's contribution mask)
                     // Transposing butterfly: 8 terms reduced over 32 lanes with 4+2+1+1+1 shuffles
                     // (instead of 8x5); lane 4*k ends up holding the warp total of term k.
                     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
@@ -300,15 +338,13 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     // term index held by this lane group: 4*b4 + 2*b3 + b2
                     if ((lane & 3) == 0) atomicAdd(&s_acc[lane >> 2][j], e0);
                     if (lane == 1) atomicAdd(&s_acc[8][j], v8);
-                    touched |= 1u << b;
                 }
             }
-            if (lane == 0 && touched) atomicOr(&s_touched[k >> 5], touched);
         }
         __syncthreads();
         {
             const int t = threadIdx.x;
-            if (t < cnt && ((s_touched[t >> 5] >> (t & 31)) & 1u)) {
+            if (t < cnt && s_cb[t]) {
                 const size_t id = s_id[t];
                 atomicAdd(dL_dmean2D + id * 3 + 0, s_acc[0][t]);
                 atomicAdd(dL_dmean2D + id * 3 + 1, s_acc[1][t]);
@@ -324,12 +360,12 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
     }
 }
 
-void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
+void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
-                       const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
-                       float* dL_dcolors, cudaStream_t s)
+                       const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                       float* dL_dopacity, float* dL_dcolors, cudaStream_t s)
 {
-    k_render_bwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix,
+    k_render_bwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib, contrib, dL_dpix,
                                          dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
 }
 
