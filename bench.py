@@ -211,14 +211,13 @@ def main():
         from gsr_mapstep import ShardedMapStep
         kfs = settings_list(dgr.GaussianRasterizationSettings, cams, bg, args.sh_degree, device)
 
-        def frame_fn(p, rs):
+        def forward_fn(p, rs):
             m2 = torch.zeros(P, 3, device=device, requires_grad=True)
             color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"],
                                                   shs=p["shs"], scales=p["scales"], rotations=p["rotations"])
-            color.backward(dL)
-            return color.detach()
+            return color, dL          # back-propagated with the fixed dL/dpix by ShardedMapStep.step
 
-        stepper = ShardedMapStep(params, frame_fn)
+        stepper = ShardedMapStep(params, forward_fn=forward_fn)
         step = lambda: stepper.step(kfs)  # noqa: E731
         launch_count = dgr._lib.gsr_launch_count
         launch_count.restype = ctypes.c_longlong

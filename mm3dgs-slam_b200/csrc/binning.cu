@@ -483,7 +483,16 @@ __global__ void __launch_bounds__(1024) k_tile_scatter(int T, const uint32_t* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t* row = base + (size_t)blockIdx.x * T;
     for (int t = tid; t < T; t += blockDim.x) s_start[t] = starts[t] + row[t];
-    for (int i = tid; i < nwarps * T; i += blockDim.x) s_cnt[i] = 0;
+    {   // zero the counters with 128-bit stores (s_cnt starts 4*T bytes into the 16-byte aligned dynamic block)
+        const size_t bytes = (size_t)nwarps * T * 2;
+        char* p = reinterpret_cast<char*>(s_cnt);
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+        for (size_t i = tid; i < head / 2 && i * 2 < bytes; i += blockDim.x) s_cnt[i] = 0;
+        const size_t body = bytes > head ? (bytes - head) / 16 : 0;
+        uint4* p4 = reinterpret_cast<uint4*>(p + head);
+        for (size_t i = tid; i < body; i += blockDim.x) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = (head + body * 16) / 2 + tid; i < bytes / 2; i += blockDim.x) s_cnt[i] = 0;
+    }
     __syncthreads();
     const uint2 seg = segs[(size_t)blockIdx.x * nwarps + warp];
     uint2* my_stream = stream + seg.x;
@@ -521,6 +530,7 @@ __global__ void __launch_bounds__(1024) k_tile_scatter(int T, const uint32_t* __
     __syncthreads();
     for (int t = tid; t < T; t += blockDim.x) {
         uint32_t run = 0;
+#pragma unroll 8
         for (int w = 0; w < nwarps; w++) {
             const uint32_t c = s_cnt[(size_t)w * T + t];
             s_cnt[(size_t)w * T + t] = (uint16_t)run;

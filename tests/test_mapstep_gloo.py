@@ -76,3 +76,22 @@ def test_sharded_equals_accumulated(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     got = torch.load(out)
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6 * float(ref.abs().max()))
+
+
+def test_two_phase_schedule_matches_per_frame():
+    """forward_fn mode (all forwards, then one autograd.backward) == frame_fn mode."""
+    from oracle import gs_oracle as O
+    gs, cams, dL, W, H = _scene()
+
+    def fwd(p, cam):
+        img = O.differentiable_render(p["means3D"], p["opacities"], p["scales"], p["rotations"], p["shs"], 0,
+                                      cam.viewmatrix, cam.projmatrix, cam.campos, torch.zeros(3), W, H, cam.tanfovx,
+                                      cam.tanfovy)
+        return img, dL.double()
+
+    a = ShardedMapStep(_params(gs), _frame_fn(dL, W, H))
+    a.step(cams)
+    b = ShardedMapStep(_params(gs), forward_fn=fwd)
+    out = b.step(cams)
+    assert len(out) == len(cams)
+    assert torch.allclose(a.bucket.flat, b.bucket.flat, rtol=1e-6, atol=1e-7 * float(a.bucket.flat.abs().max()))
