@@ -197,6 +197,8 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if distributed and args.impl == "b200":
+        # keep stdout for the one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     gs_cpu, cams, dL_cpu = build_workload(args, device)
@@ -297,7 +299,7 @@ def main():
                                 "sample": "the reference's only implementation is CUDA: compiled unmodified from "
                                           "/root/reference for sm_100a (oracle/_ref) and run on this GPU, full workload"}
         line["e2e"] = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     line["gpu_launches"] = int(n1 - n0)
@@ -382,9 +384,13 @@ def main():
         except Exception as ex:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(ex)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if distributed:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
     return 0
 
 
