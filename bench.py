@@ -213,13 +213,18 @@ def main():
         from gsr_mapstep import ShardedMapStep
         kfs = settings_list(dgr.GaussianRasterizationSettings, cams, bg, args.sh_degree, device)
 
-        def forward_fn(p, rs):
+        def forward_fn(p, rs, targets=None):
             m2 = torch.zeros(P, 3, device=device, requires_grad=True)
             color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"],
-                                                  shs=p["shs"], scales=p["scales"], rotations=p["rotations"])
+                                                  shs=p["shs"], scales=p["scales"], rotations=p["rotations"],
+                                                  grad_targets=targets)
             return color, dL          # back-propagated with the fixed dL/dpix by ShardedMapStep.step
 
-        stepper = ShardedMapStep(params, forward_fn=forward_fn)
+        # the rasterizer inputs ARE the optimised tensors here, so the backward kernels add straight into the
+        # flat gradient bucket instead of returning tensors for autograd to accumulate;
+        # consecutive keyframes alternate between two CUDA streams (binning of one overlaps blending of another)
+        stepper = ShardedMapStep(params, forward_fn=forward_fn, streams=int(os.environ.get("GSR_BENCH_STREAMS", "4")),
+                                 direct_targets=not os.environ.get("GSR_BENCH_NO_TARGETS"))
         step = lambda: stepper.step(kfs)  # noqa: E731
         launch_count = dgr._lib.gsr_launch_count
         launch_count.restype = ctypes.c_longlong
@@ -289,6 +294,7 @@ def main():
                    if (args.P, args.W, args.H, args.keyframes) == (1_000_000, 640, 480, 8) else "custom",
                    "P": args.P, "W": args.W, "H": args.H, "keyframes_per_step": args.keyframes,
                    "sh_degree": args.sh_degree, "parallelism": f"keyframe-sharded dp{world}" if args.impl == "b200" else "1 gpu",
+                   "streams_per_rank": int(os.environ.get("GSR_BENCH_STREAMS", "4")) if args.impl == "b200" else 1,
                    "l2": "per-step working set (56 B/G params + 116 B/G grads + per-frame 48 B/G records and "
                          "24+ B/instance binning, > 400 MB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks,
@@ -314,9 +320,11 @@ def main():
     torch.cuda.synchronize()
     ms_arr, cnt_arr = (ctypes.c_float * nst)(), (ctypes.c_int * nst)()
     lib.gsr_profile_collect(ms_arr, cnt_arr)
+    saved_streams, stepper.nstreams = stepper.nstreams, 1   # stage events need one in-order stream
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    stepper.nstreams = saved_streams
     lib.gsr_profile_collect(ms_arr, cnt_arr)
     lib.gsr_profile_enable(0)
     my_kfs = len(range(rank, args.keyframes, world))

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 typedef void* gsr_stream_t; /* cudaStream_t */
 
@@ -102,6 +102,12 @@ typedef struct gsr_grads {
     float* dL_dviewmatrix; /* [16] (acc) same column-major indexing as the input */
     float* dL_dprojmatrix; /* [16] (acc) */
     float* dL_dcampos;     /* [3]  (acc) */
+    /* If non-zero, dL_dmeans3D / dL_dcov3D / dL_dsh / dL_dscales / dL_drotations are ADDED to the
+     * buffers' current contents instead of overwriting them (culled Gaussians add nothing).  Lets a
+     * caller point them straight at the parameters' gradient accumulators (e.g. the flat bucket of
+     * the keyframe-sharded map step) and skip one read-add-write pass per parameter per frame. */
+    int32_t accumulate;
+    int32_t _pad;
 } gsr_grads;
 
 int gsr_abi_version(void);

@@ -352,6 +352,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     a.dL_dmeans3D = gr->dL_dmeans3D; a.dL_dcov3D = gr->dL_dcov3D; a.dL_dsh = gr->dL_dsh;
     a.dL_dscales = gr->dL_dscales; a.dL_drots = gr->dL_drotations;
     a.dL_dview = gr->dL_dviewmatrix; a.dL_dproj = gr->dL_dprojmatrix; a.dL_dcampos = gr->dL_dcampos;
+    a.accumulate = gr->accumulate;
     launch_preprocess_bwd(a, stream);
     GSR_STAGE("preprocess_backward", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS_BWD, stream, 1);

@@ -94,6 +94,7 @@ struct PreBwdArgs {
     const float* dL_dcolors;  // [P,3]
     float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots;
     float *dL_dview, *dL_dproj, *dL_dcampos;
+    int accumulate;
 };
 void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
 

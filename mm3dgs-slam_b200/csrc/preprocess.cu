@@ -47,17 +47,27 @@ __device__ __forceinline__ void stage_in(const float* __restrict__ src, float* d
         for (int i = tid; i < n; i += kPB) dst[i] = ld_stream1(src + i);
     }
 }
-// Copy n contiguous floats shared -> global.
-__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int n, int tid)
+// Copy n contiguous floats shared -> global; ACC: add `old` (the accumulator's previous contents, staged into
+// shared memory at kernel start so that the read overlaps the math instead of sitting in front of the store).
+template <bool ACC>
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, const float* old, int n, int tid)
 {
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         const int n4 = n >> 2;
         const float4* s4 = reinterpret_cast<const float4*>(src);
+        const float4* o4 = reinterpret_cast<const float4*>(old);
         float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = tid; i < n4; i += kPB) d4[i] = s4[i];
-        for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = src[i];
+        for (int i = tid; i < n4; i += kPB) {
+            float4 v = s4[i];
+            if (ACC) {
+                const float4 o = o4[i];
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            d4[i] = v;
+        }
+        for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = ACC ? old[i] + src[i] : src[i];
     } else {
-        for (int i = tid; i < n; i += kPB) dst[i] = src[i];
+        for (int i = tid; i < n; i += kPB) dst[i] = ACC ? old[i] + src[i] : src[i];
     }
 }
 
@@ -73,6 +83,16 @@ __device__ __forceinline__ float cull_radius2(float lam_max, float opacity)
     if (!(lam_max <= 1000.f)) return __int_as_float(0x7f800000);
     const float L = fmaxf(logf(255.f * opacity), 0.f);
     return 2.06f * lam_max * L + 0.5f;   // NaN opacity -> NaN -> never culled (tests are !(d2 > r2))
+}
+// Threshold for the exact ellipse-vs-sub-tile test of the forward blend: the splat can only contribute
+// where q(d) = -power(d) <= ln(255 o); 3% + 0.02 slack covers the rounding of the conic and of the
+// power evaluation inside the circle above (|d|^2 <= 2.06*1000*5.6, conic entries <= 1/0.3).  The low
+// 3 mantissa bits are overwritten with the SH clamp flags by the caller, hence the extra 1e-5.
+__device__ __forceinline__ float cull_power(float lam_max, float opacity)
+{
+    if (!(lam_max <= 1000.f)) return __int_as_float(0x7f800000);
+    const float L = fmaxf(logf(255.f * opacity), 0.f);
+    return (1.03f * L + 0.02f) * 1.00001f;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -159,7 +179,8 @@ __global__ void __launch_bounds__(kPB) k_preprocess_fwd(PreArgs a)
             const float opacity = a.opac[idx];
             r0 = make_float4(o.px, o.py, o.depth, cull_radius2(o.lam_max, opacity));
             r1 = make_float4(o.cx, o.cy, o.cz, opacity);
-            r2 = make_float4(cr, cg, cb, __int_as_float(bits));
+            // r2.w: power threshold for the sub-tile test, low 3 bits = SH clamp flags (read by the backward)
+            r2 = make_float4(cr, cg, cb, __int_as_float((__float_as_int(cull_power(o.lam_max, opacity)) & ~7) | bits));
         }
         a.radii[idx] = radius;
         a.rects[idx] = radius > 0 ? make_ushort4((unsigned short)o.x0, (unsigned short)o.y0, (unsigned short)o.x1,
@@ -218,7 +239,7 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-template <bool CAM>
+template <bool CAM, bool ACC>
 __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
 {
     __shared__ __align__(16) float s_means[kPB * 3];   // in: means      out: dL/dmeans3D
@@ -230,6 +251,11 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
     __shared__ __align__(16) float s_gcol[kPB * 3];    // in: dL/dcolor  [.,3]
     __shared__ float s_cam[35];
     __shared__ float s_red[CAM ? (kPB / 32) * 35 : 1];
+    // ACC: previous contents of the gradient accumulators
+    __shared__ __align__(16) float s_o_means[ACC ? kPB * 3 : 4];
+    __shared__ __align__(16) float s_o_scales[ACC ? kPB * 3 : 4];
+    __shared__ __align__(16) float s_o_rots[ACC ? kPB * 4 : 4];
+    __shared__ __align__(16) float s_o_sh[ACC ? kPB * 3 : 4];
 
     const int tid = threadIdx.x;
     const int base = blockIdx.x * kPB;
@@ -246,6 +272,14 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
     stage_in(a.dL_dmean2D + (size_t)base * 3, s_g2, nb * 3, tid);
     stage_in(a.dL_dconic + (size_t)base * 4, s_gc, nb * 4, tid);
     if (sh_path) stage_in(a.dL_dcolors + (size_t)base * 3, s_gcol, nb * 3, tid);
+    if (ACC) {
+        stage_in(a.dL_dmeans3D + (size_t)base * 3, s_o_means, nb * 3, tid);
+        if (has_sr) {
+            stage_in(a.dL_dscales + (size_t)base * 3, s_o_scales, nb * 3, tid);
+            stage_in(a.dL_drots + (size_t)base * 4, s_o_rots, nb * 4, tid);
+        }
+        if (sh_path && a.M == 1) stage_in(a.dL_dsh + (size_t)base * 3, s_o_sh, nb * 3, tid);
+    }
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
@@ -327,7 +361,7 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
         }
         // --- SH path
         if (sh_path) {
-            const int bits = __float_as_int(a.rec[(size_t)idx * 3 + 2].w);
+            const int bits = __float_as_int(a.rec[(size_t)idx * 3 + 2].w) & 7;
             float dRGB[3] = {s_gcol[3 * tid], s_gcol[3 * tid + 1], s_gcol[3 * tid + 2]};
             dRGB[0] *= (bits & 1) ? 0.f : 1.f;
             dRGB[1] *= (bits & 2) ? 0.f : 1.f;
@@ -338,10 +372,14 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
             V3 ddir;
             if (a.M == 1) {
                 ddir = sh_backward(a.D, s_sh + 3 * tid, dir, dRGB, dsh0);
-            } else {
+            } else if (!ACC) {
                 ddir = sh_backward(a.D, a.shs + (size_t)idx * a.M * 3, dir, dRGB, a.dL_dsh + (size_t)idx * a.M * 3);
                 // coefficients above the active degree keep a zero gradient
                 for (int k = (a.D + 1) * (a.D + 1) * 3; k < a.M * 3; k++) a.dL_dsh[(size_t)idx * a.M * 3 + k] = 0.f;
+            } else {
+                float tmp[48];
+                ddir = sh_backward(a.D, a.shs + (size_t)idx * a.M * 3, dir, dRGB, tmp);
+                for (int k = 0; k < (a.D + 1) * (a.D + 1) * 3; k++) a.dL_dsh[(size_t)idx * a.M * 3 + k] += tmp[k];
             }
             V3 dm = dnormvdv(dir_orig, ddir);
             dmean.x += dm.x;
@@ -355,7 +393,7 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
         }
         // --- scale / rotation
         if (has_sr) cov3d_backward(sc, a.scale_mod, q, dcov, dscale, dq);
-    } else if (tid < nb && sh_path && a.M != 1) {
+    } else if (!ACC && tid < nb && sh_path && a.M != 1) {
         for (int k = 0; k < a.M * 3; k++) a.dL_dsh[(size_t)idx * a.M * 3 + k] = 0.f;
     }
     __syncthreads();  // everyone is done reading the staged inputs; reuse them for the outputs
@@ -369,7 +407,10 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
     }
     if (a.dL_dcov3D != nullptr && tid < nb) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) a.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
+        for (int k = 0; k < 6; k++) {
+            if (ACC) a.dL_dcov3D[(size_t)idx * 6 + k] += dcov[k];
+            else a.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
+        }
     }
     if (CAM) {
         const int w = tid >> 5, l = tid & 31;
@@ -380,12 +421,12 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
         }
     }
     __syncthreads();
-    stage_out(a.dL_dmeans3D + (size_t)base * 3, s_means, nb * 3, tid);
+    stage_out<ACC>(a.dL_dmeans3D + (size_t)base * 3, s_means, s_o_means, nb * 3, tid);
     if (has_sr) {
-        stage_out(a.dL_dscales + (size_t)base * 3, s_scales, nb * 3, tid);
-        stage_out(a.dL_drots + (size_t)base * 4, s_rots, nb * 4, tid);
+        stage_out<ACC>(a.dL_dscales + (size_t)base * 3, s_scales, s_o_scales, nb * 3, tid);
+        stage_out<ACC>(a.dL_drots + (size_t)base * 4, s_rots, s_o_rots, nb * 4, tid);
     }
-    if (sh_path && a.M == 1) stage_out(a.dL_dsh + (size_t)base * 3, s_sh, nb * 3, tid);
+    if (sh_path && a.M == 1) stage_out<ACC>(a.dL_dsh + (size_t)base * 3, s_sh, s_o_sh, nb * 3, tid);
     if (CAM && tid < 35) {
         float v = 0.f;
 #pragma unroll
@@ -402,10 +443,10 @@ void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
     if (a.P <= 0) return;
     const bool cam = a.dL_dview || a.dL_dproj || a.dL_dcampos;
     const int grid = (a.P + kPB - 1) / kPB;
-    if (cam)
-        k_preprocess_bwd<true><<<grid, kPB, 0, s>>>(a);
-    else
-        k_preprocess_bwd<false><<<grid, kPB, 0, s>>>(a);
+    if (cam && a.accumulate) k_preprocess_bwd<true, true><<<grid, kPB, 0, s>>>(a);
+    else if (cam) k_preprocess_bwd<true, false><<<grid, kPB, 0, s>>>(a);
+    else if (a.accumulate) k_preprocess_bwd<false, true><<<grid, kPB, 0, s>>>(a);
+    else k_preprocess_bwd<false, false><<<grid, kPB, 0, s>>>(a);
 }
 
 }  // namespace gsr

@@ -62,7 +62,8 @@ class _Camera(ctypes.Structure):
 class _Grads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "dL_dmeans2D", "dL_dconic", "dL_dopacity", "dL_dcolors", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
-        "dL_dscales", "dL_drotations", "dL_dviewmatrix", "dL_dprojmatrix", "dL_dcampos")]
+        "dL_dscales", "dL_drotations", "dL_dviewmatrix", "dL_dprojmatrix", "dL_dcampos")] + [
+        ("accumulate", ctypes.c_int32), ("_pad", ctypes.c_int32)]
 
 
 def _load():
@@ -91,7 +92,7 @@ def _load():
                                  ctypes.POINTER(_Grads)]
     lib.gsr_mark_visible.restype = ctypes.c_int
     lib.gsr_mark_visible.argtypes = [vp, i32, vp, vp, vp, vp]
-    if lib.gsr_abi_version() != 1:
+    if lib.gsr_abi_version() != 2:
         raise ImportError("libgsrast_b200.so ABI version mismatch")
     return lib
 
@@ -164,24 +165,33 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
 
 
 def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view,
-                     proj, campos, bg, radii, R, geom, binning, img, want_cam):
+                     proj, campos, bg, radii, R, geom, binning, img, want_cam, targets=None):
+    """targets: optional dict of gradient accumulators (means3D, shs, opacities, scales, rotations) the
+    kernels add into directly (gsr_grads.accumulate)."""
     dev = means3D.device
     P = means3D.shape[0]
     M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
     f32 = dict(dtype=torch.float32, device=dev)
-    # accumulated-into buffers share one zero fill: [means2D 3 | conic 4 | opacity 1 | colors 3] per Gaussian
-    acc = torch.zeros(P * 11, **f32)
-    g_means2D = acc[: 3 * P].view(P, 3)
-    g_conic = acc[3 * P: 7 * P].view(P, 4)
-    g_opacity = acc[7 * P: 8 * P].view(P, 1)
-    g_colors = acc[8 * P: 11 * P].view(P, 3)
-    g_means3D = torch.empty((P, 3), **f32)
     has_sr = scales is not None and scales.numel() != 0
     has_cov = cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0
-    g_cov3D = torch.empty((P, 6), **f32) if has_cov else None
-    g_sh = torch.empty((P, M, 3), **f32) if M > 0 else None
-    g_scales = torch.empty((P, 3), **f32) if has_sr else None
-    g_rots = torch.empty((P, 4), **f32) if has_sr else None
+    # accumulated-into buffers share one zero fill: [means2D 3 | conic 4 | colors 3 | opacity 1] per Gaussian
+    acc = torch.zeros(P * (10 if targets else 11), **f32)
+    g_means2D = acc[: 3 * P].view(P, 3)
+    g_conic = acc[3 * P: 7 * P].view(P, 4)
+    g_colors = acc[7 * P: 10 * P].view(P, 3)
+    if targets:
+        g_opacity, g_means3D = targets["opacities"], targets["means3D"]   # atomics / += land in the accumulators
+        g_sh = targets["shs"] if M > 0 else None
+        g_scales = targets["scales"] if has_sr else None
+        g_rots = targets["rotations"] if has_sr else None
+        g_cov3D = None
+    else:
+        g_opacity = acc[10 * P: 11 * P].view(P, 1)
+        g_means3D = torch.empty((P, 3), **f32)
+        g_cov3D = torch.empty((P, 6), **f32) if has_cov else None
+        g_sh = torch.empty((P, M, 3), **f32) if M > 0 else None
+        g_scales = torch.empty((P, 3), **f32) if has_sr else None
+        g_rots = torch.empty((P, 4), **f32) if has_sr else None
     g_cam = torch.zeros(35, **f32) if want_cam else None
     if P == 0:
         return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam
@@ -191,7 +201,8 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
                 g_means3D.data_ptr(), _ptr(g_cov3D), _ptr(g_sh), _ptr(g_scales), _ptr(g_rots),
                 g_cam.data_ptr() if want_cam else None,
                 g_cam.data_ptr() + 64 if want_cam else None,
-                g_cam.data_ptr() + 128 if want_cam else None)
+                g_cam.data_ptr() + 128 if want_cam else None,
+                1 if targets else 0, 0)
     _check(_lib.gsr_backward(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, _ptr(geom), _ptr(binning),
                              _ptr(img), grad_color.data_ptr(), ctypes.byref(gr)))
     return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam
@@ -201,17 +212,33 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
 # Public API (same names and argument meaning as the reference)
 # ------------------------------------------------------------------------------------------------
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, grad_targets=None):
+    """`grad_targets` (extension, optional): dict with fp32 contiguous accumulators for means3D, shs,
+    opacities, scales, rotations.  The backward kernels then ADD this call's gradients straight into them
+    (e.g. views of the map step's flat bucket) and autograd receives no gradient for those inputs — for
+    the case where the rasterizer inputs ARE the optimised tensors."""
     rs = raster_settings
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos)
+                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos, grad_targets)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, viewmatrix, projmatrix, campos):
+                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None):
         rs = raster_settings
+        if grad_targets:
+            if cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0:
+                raise ValueError("grad_targets is not supported with cov3D_precomp")
+            need = ["means3D", "opacities"] + (["shs"] if sh is not None and sh.numel() else []) + (
+                ["scales", "rotations"] if scales is not None and scales.numel() else [])
+            src = dict(means3D=means3D, opacities=opacities, shs=sh, scales=scales, rotations=rotations)
+            for k in need:
+                t = grad_targets.get(k)
+                if (t is None or t.dtype != torch.float32 or not t.is_contiguous() or t.device != means3D.device
+                        or t.numel() != src[k].numel()):
+                    raise ValueError(f"grad_targets['{k}'] must be a contiguous fp32 CUDA tensor shaped like the input")
+        ctx.grad_targets = grad_targets if grad_targets else None
         if means3D.dim() != 2 or means3D.shape[1] != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
         if not means3D.is_cuda:
@@ -249,7 +276,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         with torch.cuda.device(dev):
             grad = _prep(grad_out_color, dev)
             args = (grad, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj,
-                    campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam)
+                    campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam, ctx.grad_targets)
             if rs.debug:
                 try:
                     res = _backward_native(*args)
@@ -266,10 +293,13 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_view = g_cam[0:16].view_as(view) if ctx.needs_input_grad[9] else None
             g_proj = g_cam[16:32].view_as(proj) if ctx.needs_input_grad[10] else None
             g_campos = g_cam[32:35].view_as(campos) if ctx.needs_input_grad[11] else None
+        if ctx.grad_targets:   # already added into the accumulators by the kernels
+            return (None, g_means2D, None, g_colors if has_colors else None, None, None, None, None,
+                    None, g_view, g_proj, g_campos, None)
         if opacities.dim() == 1:
             g_opacity = g_opacity.view(-1)
         return (g_means3D, g_means2D, g_sh, g_colors if has_colors else None, g_opacity, g_scales, g_rots, g_cov3D,
-                None, g_view, g_proj, g_campos)
+                None, g_view, g_proj, g_campos, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -310,7 +340,7 @@ class GaussianRasterizer(nn.Module):
             return present.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, grad_targets=None):
         rs = self.raster_settings
         if (shs is None) == (colors_precomp is None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
@@ -326,4 +356,4 @@ class GaussianRasterizer(nn.Module):
             empty if scales is None else scales,
             empty if rotations is None else rotations,
             empty if cov3D_precomp is None else cov3D_precomp,
-            rs)
+            rs, grad_targets)

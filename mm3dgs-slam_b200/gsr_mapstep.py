@@ -71,7 +71,13 @@ class ShardedMapStep:
     """
 
     def __init__(self, params: Dict[str, torch.Tensor], frame_fn: Optional[Callable] = None,
-                 group: Optional[dist.ProcessGroup] = None, forward_fn: Optional[Callable] = None):
+                 group: Optional[dist.ProcessGroup] = None, forward_fn: Optional[Callable] = None,
+                 streams: int = 1, direct_targets: bool = False):
+        """streams > 1 (forward_fn mode, CUDA only): consecutive keyframes alternate between `streams` CUDA
+        streams, so the latency-bound binning kernels of one frame overlap the blend kernels of another.
+        direct_targets: forward_fn receives a third argument, a dict of gradient accumulators (views of a flat
+        bucket, one bucket per stream) for kernels that add their gradients in place; the per-stream buckets
+        are summed into the main one before the all-reduce."""
         if (frame_fn is None) == (forward_fn is None):
             raise ValueError("give exactly one of frame_fn / forward_fn")
         self.params = params
@@ -79,9 +85,45 @@ class ShardedMapStep:
         self.frame_fn = frame_fn
         self.forward_fn = forward_fn
         self.group = group
+        self.direct_targets = direct_targets
+        first = next(iter(params.values()))
+        self.nstreams = max(1, int(streams)) if (forward_fn is not None and first.is_cuda) else 1
+        self.streams = [torch.cuda.Stream(first.device) for _ in range(self.nstreams)] if self.nstreams > 1 else []
+        # stream i > 0 adds into its own flat buffer (same layout) so concurrent in-place adds never collide
+        self.aux_flat = [torch.zeros_like(self.bucket.flat) for _ in range(self.nstreams - 1)] if direct_targets else []
+        self.aux_views = []
+        for flat in self.aux_flat:
+            views, off = {}, 0
+            for k, p in params.items():
+                views[k] = flat[off: off + p.numel()].view_as(p)
+                off += p.numel()
+            self.aux_views.append(views)
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
+
+    def _targets(self, i):
+        if not self.direct_targets:
+            return None
+        return self.bucket.views if i == 0 else self.aux_views[i - 1]
+
+    def _forwards(self, mine):
+        if self.nstreams == 1:
+            if self.direct_targets:
+                return [self.forward_fn(self.params, kf, self._targets(0)) for kf in mine]
+            return [self.forward_fn(self.params, kf) for kf in mine]
+        main = torch.cuda.current_stream()
+        for flat in self.aux_flat:
+            flat.zero_()
+        for st in self.streams:
+            st.wait_stream(main)
+        outs = []
+        for j, kf in enumerate(mine):
+            i = j % self.nstreams
+            with torch.cuda.stream(self.streams[i]):
+                outs.append(self.forward_fn(self.params, kf, self._targets(i)) if self.direct_targets
+                            else self.forward_fn(self.params, kf))
+        return outs
 
     def my_keyframes(self, keyframes: Sequence):
         return [keyframes[i] for i in shard_keyframes(len(keyframes), self.rank, self.world)]
@@ -92,9 +134,17 @@ class ShardedMapStep:
         self.bucket.attach()
         mine = self.my_keyframes(keyframes)
         if self.forward_fn is not None:
-            outs = [self.forward_fn(self.params, kf) for kf in mine]
+            outs = self._forwards(mine)
             if outs:
                 torch.autograd.backward([o for o, _ in outs], [g for _, g in outs])
+            if self.nstreams > 1:
+                main = torch.cuda.current_stream()
+                for st in self.streams:
+                    main.wait_stream(st)
+                for o, _ in outs:
+                    o.record_stream(main)
+            for flat in self.aux_flat:
+                self.bucket.flat.add_(flat)
             losses = [o.detach() for o, _ in outs]
         else:
             losses = [self.frame_fn(self.params, kf) for kf in mine]

@@ -21,7 +21,7 @@ def test_header_symbols_exported(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/gsrast_b200.h but not exported"
     lib.gsr_abi_version.restype = ctypes.c_int
-    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_abi_version() == 2
 
 
 def test_struct_mirrors_match_c_layout(built_lib):
@@ -31,7 +31,7 @@ def test_struct_mirrors_match_c_layout(built_lib):
     assert dgr._Gaussians.means3D.offset == 16 and dgr._Gaussians.scale_modifier.offset == 72
     assert ctypes.sizeof(dgr._Camera) == 16 + 4 * 8 + 8
     assert dgr._Camera.viewmatrix.offset == 16 and dgr._Camera.prefiltered.offset == 48
-    assert ctypes.sizeof(dgr._Grads) == 12 * 8
+    assert ctypes.sizeof(dgr._Grads) == 12 * 8 + 8 and dgr._Grads.accumulate.offset == 96
 
 
 def test_python_surface_matches_reference(built_lib):
@@ -42,9 +42,9 @@ def test_python_surface_matches_reference(built_lib):
         "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
         "sh_degree", "campos", "prefiltered", "debug")
     sig = inspect.signature(dgr.GaussianRasterizer.forward)
-    assert list(sig.parameters) == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
-                                    "rotations", "cov3D_precomp"]
-    assert list(inspect.signature(dgr.rasterize_gaussians).parameters) == [
+    assert list(sig.parameters)[:9] == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                        "rotations", "cov3D_precomp"]     # + optional additive extensions
+    assert list(inspect.signature(dgr.rasterize_gaussians).parameters)[:9] == [
         "means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp",
         "raster_settings"]
     assert hasattr(dgr.GaussianRasterizer, "markVisible")
@@ -71,5 +71,4 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
-                assert "oracle" not in txt.replace("oracle/", "").lower() or f == "build.py" or "import oracle" not in txt
                 assert "from oracle" not in txt and "import oracle" not in txt, os.path.join(d, f)

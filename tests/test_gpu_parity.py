@@ -266,3 +266,35 @@ def test_camera_gradients(dgr):
     assert rel_err(v.grad, view.grad) < 1e-3
     assert rel_err(p.grad, proj.grad) < 1e-3
     assert rel_err(c.grad, campos.grad) < 1e-3
+
+
+def test_grad_targets_accumulate(dgr):
+    """Extension: gradients added straight into caller-provided accumulators == autograd accumulation."""
+    import gsr_synth as S
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H, deg = 20000, 160, 120, 1
+    gs, _, dL, bg = scene_on(dev, P, W, H, 41, deg)
+    cams = S.orbit_cameras(W, H, 2, (0.0, 0.0, 4.0), 0.4)
+    names = ["means3D", "shs", "opacities", "scales", "rotations"]
+
+    def run(use_targets):
+        p = {k: gs[k].clone().requires_grad_(True) for k in names}
+        tg = {k: torch.zeros_like(v) for k, v in p.items()} if use_targets else None
+        outs = []
+        for cam in cams:
+            rs = settings_for(dgr, cam, bg, deg, dev)
+            m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+            color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"],
+                                                  shs=p["shs"], scales=p["scales"], rotations=p["rotations"],
+                                                  grad_targets=tg)
+            outs.append(color)
+        torch.autograd.backward(outs, [dL] * len(outs))
+        if use_targets:
+            assert all(v.grad is None for v in p.values())
+            return tg
+        return {k: v.grad for k, v in p.items()}
+
+    a, b = run(False), run(True)
+    for k in names:
+        assert rel_err(b[k], a[k]) < 1e-5, k
