@@ -15,10 +15,13 @@
 //    so exactly the same (pixel, splat) pairs contribute as in the reference;
 //  * early termination is per warp (__all_sync on the running transmittance), the CTA leaves when
 //    all 8 warps are done;
+//  * the forward records, per list entry, which of the tile's 8 warps blended it for at least one
+//    pixel (one byte per entry);
 //  * backward: the traversal starts at the CTA-wide last contributor instead of the end of the
-//    list, the 9 per-splat gradient terms are reduced over the warp with shuffles, combined over
-//    the 8 warps in shared memory, and leave the CTA as ONE red.global per (tile, splat, term)
-//    instead of one atomicAdd per (pixel, splat, term).
+//    list and each warp visits exactly the entries it blended in the forward (no culling test, no
+//    wasted evaluation); the 9 per-splat gradient terms are reduced over the warp with a transposing
+//    butterfly (14 shuffles instead of 45) and leave as ONE fire-and-forget RED.ADD.F32 per
+//    (warp, splat, term) instead of one atomicAdd per (pixel, splat, term).
 #include "gsr_internal.cuh"
 
 namespace gsr {
@@ -242,7 +245,6 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
     __shared__ float4 s_r1[kBatch];
     __shared__ float4 s_r2[kBatch];
     __shared__ uint32_t s_id[kBatch];
-    __shared__ float s_acc[9][kBatch];   // per staged splat: m2x m2y cx cy cw op cr cg cb
     __shared__ uint8_t s_cb[kBatch];     // forward's contribution byte: bit w <=> warp w blended this entry
     __shared__ uint32_t s_max;
 
@@ -267,6 +269,16 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;  // last colour / alpha
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    // role of this lane after the butterfly: lane 4k holds term k (k < 8), lane 1 holds term 8
+    float* red_base = nullptr;
+    int red_stride = 0;
+    {
+        const int k = (lane == 1) ? 8 : (((lane & 3) == 0) ? (lane >> 2) : -1);
+        if (k == 0 || k == 1) { red_base = dL_dmean2D + k; red_stride = 3; }
+        else if (k >= 2 && k <= 4) { red_base = dL_dconic + (k == 4 ? 3 : k - 2); red_stride = 4; }
+        else if (k == 5) { red_base = dL_dopacity; red_stride = 1; }
+        else if (k >= 6) { red_base = dL_dcolors + (k - 6); red_stride = 3; }
+    }
 
     const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
     if (threadIdx.x == 0) s_max = 0;
@@ -295,8 +307,6 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                 }
             }
             s_cb[t] = cb;
-#pragma unroll
-            for (int k = 0; k < 9; k++) s_acc[k][t] = 0.f;
         }
         __syncthreads();
         // first slot this warp cares about: position < wmax  <=>  t > hi-1-wmax
@@ -366,25 +376,9 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     e0 += __shfl_xor_sync(kFull, e0, 1);
                     v8 = warp_sum(v8);
                     // term index held by this lane group: 4*b4 + 2*b3 + b2
-                    if ((lane & 3) == 0) atomicAdd(&s_acc[lane >> 2][j], e0);
-                    if (lane == 1) atomicAdd(&s_acc[8][j], v8);
+                    // one fire-and-forget RED.ADD.F32 per (warp, splat, term), issued by the 9 lanes that hold a total
+                    if (red_base != nullptr) atomicAdd(red_base + (size_t)s_id[j] * red_stride, lane == 1 ? v8 : e0);
                 }
-            }
-        }
-        __syncthreads();
-        {
-            const int t = threadIdx.x;
-            if (t < cnt && s_cb[t]) {
-                const size_t id = s_id[t];
-                atomicAdd(dL_dmean2D + id * 3 + 0, s_acc[0][t]);
-                atomicAdd(dL_dmean2D + id * 3 + 1, s_acc[1][t]);
-                atomicAdd(dL_dconic + id * 4 + 0, s_acc[2][t]);
-                atomicAdd(dL_dconic + id * 4 + 1, s_acc[3][t]);
-                atomicAdd(dL_dconic + id * 4 + 3, s_acc[4][t]);
-                atomicAdd(dL_dopacity + id, s_acc[5][t]);
-                atomicAdd(dL_dcolors + id * 3 + 0, s_acc[6][t]);
-                atomicAdd(dL_dcolors + id * 3 + 1, s_acc[7][t]);
-                atomicAdd(dL_dcolors + id * 3 + 2, s_acc[8][t]);
             }
         }
     }
