@@ -175,6 +175,47 @@ def cpu_baseline(args, gs, cam, dL, tile_stride=12):
             "est_seconds_per_frame": est}
 
 
+def measure_m2(rasterize, settings_cls, params, dL, device, args, fused=None, iters=6):
+    """Secondary metric M2: one full SLAM render — the reference renderer's call pattern
+    restated in tests/slam_glue.py (python-side pose transform, RGB pass + depth/silhouette pass sharing one
+    means2D leaf) — plus backward of a scalar loss, frames/s.  `fused`: GaussianRasterizer class to also time
+    the single-call extra_colors path."""
+    from tests import slam_glue
+    P, W, H = args.P, args.W, args.H
+    bg = torch.zeros(3, device=device)
+    rs = slam_glue.settings(settings_cls, W, H, bg, args.sh_degree, device)
+    w2c = S.look_at_w2c((0.3, -0.1, 0.2), (0.0, 0.0, 4.0)).to(device)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+
+    def two_pass():
+        pose = w2c.clone().requires_grad_(True)
+        rgb, depth, _, _ = slam_glue.render_two_pass(rasterize, rs, p, pose)
+        ((rgb * dL).sum() + (depth * dL).sum()).backward()
+
+    def one_pass():
+        pose = w2c.clone().requires_grad_(True)
+        mc = slam_glue.camera_frame(p, pose)
+        m2 = torch.zeros_like(mc, requires_grad=True)
+        rgb, depth, _ = fused(rs)(means3D=mc, means2D=m2, opacities=p["opacities"], shs=p["shs"], scales=p["scales"],
+                                  rotations=p["rotations"], extra_colors=slam_glue.depth_silhouette(mc))
+        ((rgb * dL).sum() + (depth * dL).sum()).backward()
+
+    out = {}
+    for name, fn in (("two_pass", two_pass),) + ((("fused_rgbd", one_pass),) if fused is not None else ()):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_fps"] = iters / (e0.elapsed_time(e1) / 1e3)
+    out["what"] = "full SLAM render (pose transform + RGB + depth/silhouette) fwd+bwd, 1 GPU, same scene"
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -305,6 +346,11 @@ def main():
                                 "sample": "the reference's only implementation is CUDA: compiled unmodified from "
                                           "/root/reference for sm_100a (oracle/_ref) and run on this GPU, full workload"}
         line["e2e"] = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        try:
+            line["m2"] = measure_m2(lambda m3, m2, op, rs_, **kw: ref_api.rasterize(m3, m2, op, rs_, **kw), RS, params,
+                                    dL, device, args)
+        except Exception as ex:
+            line["m2"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -386,6 +432,13 @@ def main():
                        "what": "pinned-host Gaussian parameters copied in, 8-keyframe step through GaussianRasterizer, "
                                "gradient bucket + rendered images copied back to pinned host memory, every step"}
 
+    if rank == 0 and world == 1:
+        try:
+            line["m2"] = measure_m2(
+                lambda m3, m2, op, rs_, **kw: dgr.GaussianRasterizer(rs_)(means3D=m3, means2D=m2, opacities=op, **kw),
+                dgr.GaussianRasterizationSettings, params, dL, device, args, fused=dgr.GaussianRasterizer)
+        except Exception as ex:
+            line["m2"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args, gs_cpu, cams[0], dL_cpu)

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 2
+#define GSR_ABI_VERSION 3
 
 typedef void* gsr_stream_t; /* cudaStream_t */
 
@@ -69,6 +69,10 @@ typedef struct gsr_gaussians {
     const float* cov3D_precomp; /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
     float scale_modifier;
     int32_t _pad2;
+    /* Extension: [P,3] extra per-Gaussian colours blended in the SAME pass into a second
+     * [3,H,W] image (the SLAM renderer's depth / silhouette colours [z, 1, z^2], for which the reference
+     * runs the whole rasterizer a second time, R/slam/renderer.py:207-214).  NULL = absent. */
+    const float* extra_colors;
 } gsr_gaussians;
 
 /* Camera + raster settings (reference: GaussianRasterizationSettings, __init__.py:157-169). */
@@ -108,6 +112,7 @@ typedef struct gsr_grads {
      * the keyframe-sharded map step) and skip one read-add-write pass per parameter per frame. */
     int32_t accumulate;
     int32_t _pad;
+    float* dL_dextra;      /* [P,3] (acc) gradient w.r.t. extra_colors; required iff extra_colors is given */
 } gsr_grads;
 
 int gsr_abi_version(void);
@@ -134,13 +139,14 @@ int gsr_forward_preprocess(gsr_stream_t stream, const gsr_gaussians* g, const gs
 int gsr_forward_render(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                        const int32_t* radii, int64_t R,
                        void* geom_ws, void* binning_ws, size_t binning_ws_bytes, void* img_ws,
-                       float* out_color);
+                       float* out_color, float* out_extra /* [3,H,W]; required iff g->extra_colors */);
 
 /* Backward of the whole call. */
 int gsr_backward(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                  const int32_t* radii, int64_t R,
                  const void* geom_ws, const void* binning_ws, const void* img_ws,
-                 const float* dL_dpixels /* [3,H,W] */, const gsr_grads* grads);
+                 const float* dL_dpixels /* [3,H,W] */, const float* dL_dpixels_extra /* [3,H,W] or NULL */,
+                 const gsr_grads* grads);
 
 /* present[i] = 1 if Gaussian i passes the near-plane test (z_view > 0.1). */
 int gsr_mark_visible(gsr_stream_t stream, int32_t P, const float* means3D, const float* viewmatrix,

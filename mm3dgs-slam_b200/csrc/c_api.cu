@@ -129,14 +129,17 @@ BinWS bin_ws_carve(char* base, int64_t R)
     return w;
 }
 
-// Pinned 4-byte slot + event per host thread for the one device->host hand-off of R.
+// Pinned 4-byte slot + event per (host thread, device) for the one device->host hand-off of R.
 struct HostSlot {
     int32_t* pinned = nullptr;
     cudaEvent_t ev = nullptr;
 };
 static HostSlot& host_slot()
 {
-    static thread_local HostSlot s;
+    static thread_local HostSlot slots[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    HostSlot& s = slots[dev];
     if (!s.pinned) {
         if (cudaHostAlloc((void**)&s.pinned, 64, cudaHostAllocDefault) != cudaSuccess) s.pinned = nullptr;
         if (cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) != cudaSuccess) s.ev = nullptr;
@@ -282,15 +285,17 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
 
 int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera* cam, const int32_t* radii,
                        int64_t R, void* geom_ws, void* binning_ws, size_t binning_ws_bytes, void* img_ws,
-                       float* out_color)
+                       float* out_color, float* out_extra)
 {
     if (int rc = check_common(g, cam)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int P = g->P, W = cam->width, H = cam->height;
     if (!out_color) return fail(GSR_ERR_INVALID, "out_color required");
+    if (g->extra_colors && !out_extra) return fail(GSR_ERR_INVALID, "out_extra required with extra_colors");
     if (R < 0 || R > 0x7fffffffLL) return fail(GSR_ERR_INVALID, "num_rendered out of range");
     if (P == 0) {  // reference: zero image, nothing else (DGR/rasterize_points.cu:81)
         GSR_CUDA(cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * (size_t)W * H, stream));
+        if (out_extra) GSR_CUDA(cudaMemsetAsync(out_extra, 0, sizeof(float) * 3 * (size_t)W * H, stream));
         return GSR_OK;
     }
     if (!radii || !geom_ws || !img_ws || (R > 0 && !binning_ws))
@@ -307,7 +312,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 4);
     launch_render_fwd(W, H, gx, gy, iw.ranges, iw.order, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
-                      out_color, bw.contrib, stream);
+                      out_color, bw.contrib, g->extra_colors, out_extra, stream);
     GSR_STAGE("render", cam->debug, stream);
     GSR_MARK(ST_RENDER, stream, 1);
     return GSR_OK;
@@ -315,7 +320,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
 
 int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera* cam, const int32_t* radii, int64_t R,
                  const void* geom_ws, const void* binning_ws, const void* img_ws, const float* dL_dpixels,
-                 const gsr_grads* gr)
+                 const float* dL_dpixels_extra, const gsr_grads* gr)
 {
     if (int rc = check_common(g, cam)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -324,6 +329,8 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     if (!gr || !dL_dpixels || !radii || !geom_ws || !img_ws) return fail(GSR_ERR_INVALID, "null argument");
     if (!gr->dL_dmeans2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolors || !gr->dL_dmeans3D)
         return fail(GSR_ERR_INVALID, "required gradient buffer missing");
+    if (g->extra_colors && (!dL_dpixels_extra || !gr->dL_dextra))
+        return fail(GSR_ERR_INVALID, "dL_dpixels_extra / dL_dextra required with extra_colors");
     const int M = g->shs ? g->sh_coeffs : 0;
     if ((M > 0 && !gr->dL_dsh) || (g->scales && (!gr->dL_dscales || !gr->dL_drotations)))
         return fail(GSR_ERR_INVALID, "gradient buffer for a provided input missing");
@@ -336,7 +343,8 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
         if (!binning_ws) return fail(GSR_ERR_INVALID, "binning workspace required");
         BinWS bw = bin_ws_carve((char*)binning_ws, R);
         launch_render_bwd(W, H, gx, gy, iw.ranges, iw.order, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
-                          bw.contrib, dL_dpixels, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolors, stream);
+                          bw.contrib, dL_dpixels, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolors,
+                          g->extra_colors, dL_dpixels_extra, gr->dL_dextra, stream);
         GSR_STAGE("render_backward", cam->debug, stream);
         GSR_MARK(ST_RENDER_BWD, stream, 1);
     }

@@ -77,11 +77,12 @@ int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
-                       uint8_t* contrib, cudaStream_t s);
+                       uint8_t* contrib, const float* extra, float* out_extra, cudaStream_t s);
 void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
                        const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
-                       float* dL_dopacity, float* dL_dcolors /*[P,3]*/, cudaStream_t s);
+                       float* dL_dopacity, float* dL_dcolors /*[P,3]*/, const float* extra, const float* dL_dpix_extra,
+                       float* dL_dextra, cudaStream_t s);
 
 struct PreBwdArgs {
     int P, D, M, W, H;

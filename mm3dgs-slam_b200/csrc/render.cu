@@ -98,16 +98,21 @@ __device__ __forceinline__ bool subtile_hit_ellipse(const TileGeom& g, float cx,
 // ----------------------------------------------------------------------------------------------
 // Forward
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, GSR_FWD_MIN_CTAS) k_render_fwd(int W, int H, int gx, const uint2* __restrict__ ranges,
-                                                    const uint32_t* __restrict__ order,
-                                                    const uint32_t* __restrict__ point_list,
-                                                    const float4* __restrict__ rec, const float* __restrict__ bg,
-                                                    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                                                    float* __restrict__ out_color, uint8_t* __restrict__ contrib)
+// EXTRA: three more colour channels per splat (`extra` [P,3], e.g. the SLAM renderer's depth /
+// silhouette colours [z, 1, z^2]) are blended in the same pass into `out_extra` [3,H,W] — one
+// preprocess + one sort + one traversal instead of the reference's second full rasterizer call
+// (R/slam/renderer.py:196-214).
+template <bool EXTRA>
+__global__ void __launch_bounds__(256, EXTRA ? 6 : GSR_FWD_MIN_CTAS) k_render_fwd(
+    int W, int H, int gx, const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+    const uint32_t* __restrict__ point_list, const float4* __restrict__ rec, const float* __restrict__ bg,
+    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+    uint8_t* __restrict__ contrib, const float* __restrict__ extra, float* __restrict__ out_extra)
 {
     __shared__ float4 s_r0[kBatch];  // px, py, depth, cull r^2
     __shared__ float4 s_r1[kBatch];  // conic xyz, opacity
     __shared__ float4 s_r2[kBatch];  // rgb, bits
+    __shared__ float s_ex[EXTRA ? kBatch * 3 : 1];
     __shared__ uint32_t s_mask[2][kBatch / 32][8];   // [buffer][32-entry group][warp]: entries this warp blended
 
     const int tile = GSR_TILE_OF_BLOCK;
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__(256, GSR_FWD_MIN_CTAS) k_render_fwd(int W, int
 
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float E0 = 0.f, E1 = 0.f, E2 = 0.f;
     uint32_t last_contributor = 0;
     bool done = !g.inside;
     bool warp_done = __all_sync(kFull, done);
@@ -146,6 +152,12 @@ __global__ void __launch_bounds__(256, GSR_FWD_MIN_CTAS) k_render_fwd(int W, int
             s_r0[threadIdx.x] = __ldg(r);
             s_r1[threadIdx.x] = __ldg(r + 1);
             s_r2[threadIdx.x] = __ldg(r + 2);
+            if (EXTRA) {
+                const float* e = extra + (size_t)id * 3;
+                s_ex[3 * threadIdx.x + 0] = __ldg(e);
+                s_ex[3 * threadIdx.x + 1] = __ldg(e + 1);
+                s_ex[3 * threadIdx.x + 2] = __ldg(e + 2);
+            }
         }
         if (threadIdx.x < 64) s_mask[buf][threadIdx.x >> 3][threadIdx.x & 7] = 0u;
         __syncthreads();
@@ -187,6 +199,11 @@ __global__ void __launch_bounds__(256, GSR_FWD_MIN_CTAS) k_render_fwd(int W, int
                         C0 += c.x * w;
                         C1 += c.y * w;
                         C2 += c.z * w;
+                        if (EXTRA) {
+                            E0 += s_ex[3 * j + 0] * w;
+                            E1 += s_ex[3 * j + 1] * w;
+                            E2 += s_ex[3 * j + 2] * w;
+                        }
                         T = test_T;
                         last_contributor = (uint32_t)(base + j + 1);
                         blended |= 1u << bit;
@@ -209,15 +226,24 @@ __global__ void __launch_bounds__(256, GSR_FWD_MIN_CTAS) k_render_fwd(int W, int
         out_color[pix] = C0 + T * bg[0];
         out_color[HW + pix] = C1 + T * bg[1];
         out_color[2 * HW + pix] = C2 + T * bg[2];
+        if (EXTRA) {
+            out_extra[pix] = E0 + T * bg[0];
+            out_extra[HW + pix] = E1 + T * bg[1];
+            out_extra[2 * HW + pix] = E2 + T * bg[2];
+        }
     }
 }
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
-                       uint8_t* contrib, cudaStream_t s)
+                       uint8_t* contrib, const float* extra, float* out_extra, cudaStream_t s)
 {
-    k_render_fwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib, out_color,
-                                         contrib);
+    if (extra != nullptr)
+        k_render_fwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+                                                   out_color, contrib, extra, out_extra);
+    else
+        k_render_fwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+                                                    out_color, contrib, nullptr, nullptr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -230,6 +256,7 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+template <bool EXTRA>
 __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
                                                     const uint32_t* __restrict__ order,
                                                     const uint32_t* __restrict__ point_list,
@@ -239,11 +266,14 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                                                     const uint8_t* __restrict__ contrib,
                                                     const float* __restrict__ dL_dpix, float* __restrict__ dL_dmean2D,
                                                     float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
-                                                    float* __restrict__ dL_dcolors)
+                                                    float* __restrict__ dL_dcolors, const float* __restrict__ extra,
+                                                    const float* __restrict__ dL_dpix_extra,
+                                                    float* __restrict__ dL_dextra)
 {
     __shared__ float4 s_r0[kBatch];
     __shared__ float4 s_r1[kBatch];
     __shared__ float4 s_r2[kBatch];
+    __shared__ float s_ex[EXTRA ? kBatch * 3 : 1];
     __shared__ uint32_t s_id[kBatch];
     __shared__ uint8_t s_cb[kBatch];     // forward's contribution byte: bit w <=> warp w blended this entry
     __shared__ uint32_t s_max;
@@ -265,9 +295,16 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
         dLp1 = dL_dpix[HW + pix];
         dLp2 = dL_dpix[2 * HW + pix];
     }
-    const float bg_dot_dpixel = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+    float dLe0 = 0.f, dLe1 = 0.f, dLe2 = 0.f;
+    if (EXTRA && g.inside) {
+        dLe0 = dL_dpix_extra[pix];
+        dLe1 = dL_dpix_extra[HW + pix];
+        dLe2 = dL_dpix_extra[2 * HW + pix];
+    }
+    const float bg_dot_dpixel = bg[0] * (dLp0 + dLe0) + bg[1] * (dLp1 + dLe1) + bg[2] * (dLp2 + dLe2);
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;  // last colour / alpha
+    float acc3 = 0.f, acc4 = 0.f, acc5 = 0.f, lc3 = 0.f, lc4 = 0.f, lc5 = 0.f;   // same for the extra channels
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     // role of this lane after the butterfly: lane 4k holds term k (k < 8), lane 1 holds term 8
     float* red_base = nullptr;
@@ -279,6 +316,9 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
         else if (k == 5) { red_base = dL_dopacity; red_stride = 1; }
         else if (k >= 6) { red_base = dL_dcolors + (k - 6); red_stride = 3; }
     }
+    // EXTRA: second 4-term butterfly (colour b + 3 extra channels) ends in lanes 0, 8, 16, 24
+    float* red2_base = nullptr;
+    if (EXTRA && (lane & 7) == 0) red2_base = (lane == 0) ? dL_dcolors + 2 : dL_dextra + ((lane >> 3) - 1);
 
     const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
     if (threadIdx.x == 0) s_max = 0;
@@ -304,6 +344,12 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     s_r0[t] = __ldg(r);
                     s_r1[t] = __ldg(r + 1);
                     s_r2[t] = __ldg(r + 2);
+                    if (EXTRA) {
+                        const float* e = extra + (size_t)id * 3;
+                        s_ex[3 * t + 0] = __ldg(e);
+                        s_ex[3 * t + 1] = __ldg(e + 1);
+                        s_ex[3 * t + 2] = __ldg(e + 2);
+                    }
                 }
             }
             s_cb[t] = cb;
@@ -329,6 +375,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                 const float alpha = fminf(0.99f, co.w * G);
                 const bool live = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                 float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
+                float v9 = 0.f, v10 = 0.f, v11 = 0.f;
                 if (live) {
                     const float4 c = s_r2[j];
                     const float inv_1ma = __frcp_rn(1.f - alpha);
@@ -347,6 +394,21 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     v6 = dchannel_dcolor * dLp0;
                     v7 = dchannel_dcolor * dLp1;
                     v8 = dchannel_dcolor * dLp2;
+                    if (EXTRA) {
+                        const float e0c = s_ex[3 * j + 0], e1c = s_ex[3 * j + 1], e2c = s_ex[3 * j + 2];
+                        acc3 = last_alpha * lc3 + (1.f - last_alpha) * acc3;
+                        lc3 = e0c;
+                        dL_dalpha += (e0c - acc3) * dLe0;
+                        acc4 = last_alpha * lc4 + (1.f - last_alpha) * acc4;
+                        lc4 = e1c;
+                        dL_dalpha += (e1c - acc4) * dLe1;
+                        acc5 = last_alpha * lc5 + (1.f - last_alpha) * acc5;
+                        lc5 = e2c;
+                        dL_dalpha += (e2c - acc5) * dLe2;
+                        v9 = dchannel_dcolor * dLe0;
+                        v10 = dchannel_dcolor * dLe1;
+                        v11 = dchannel_dcolor * dLe2;
+                    }
                     dL_dalpha *= T;
                     last_alpha = alpha;
                     dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
@@ -374,10 +436,21 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
                     float e0 = (b2 ? c1 : c0) + __shfl_xor_sync(kFull, b2 ? c0 : c1, 4);
                     e0 += __shfl_xor_sync(kFull, e0, 2);
                     e0 += __shfl_xor_sync(kFull, e0, 1);
-                    v8 = warp_sum(v8);
                     // term index held by this lane group: 4*b4 + 2*b3 + b2
-                    // one fire-and-forget RED.ADD.F32 per (warp, splat, term), issued by the 9 lanes that hold a total
-                    if (red_base != nullptr) atomicAdd(red_base + (size_t)s_id[j] * red_stride, lane == 1 ? v8 : e0);
+                    // one fire-and-forget RED.ADD.F32 per (warp, splat, term), issued by the lanes that hold a total
+                    if (EXTRA) {
+                        float f0 = (b4 ? v10 : v8) + __shfl_xor_sync(kFull, b4 ? v8 : v10, 16);
+                        float f1 = (b4 ? v11 : v9) + __shfl_xor_sync(kFull, b4 ? v9 : v11, 16);
+                        float h0 = (b3 ? f1 : f0) + __shfl_xor_sync(kFull, b3 ? f0 : f1, 8);
+                        h0 += __shfl_xor_sync(kFull, h0, 4);
+                        h0 += __shfl_xor_sync(kFull, h0, 2);
+                        h0 += __shfl_xor_sync(kFull, h0, 1);   // lanes with (b4, b3): term 8 + 2*b4 + b3
+                        if (red_base != nullptr && lane != 1) atomicAdd(red_base + (size_t)s_id[j] * red_stride, e0);
+                        if (red2_base != nullptr) atomicAdd(red2_base + (size_t)s_id[j] * 3, h0);
+                    } else {
+                        v8 = warp_sum(v8);
+                        if (red_base != nullptr) atomicAdd(red_base + (size_t)s_id[j] * red_stride, lane == 1 ? v8 : e0);
+                    }
                 }
             }
         }
@@ -387,10 +460,17 @@ __global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const 
 void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
                        const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
-                       float* dL_dopacity, float* dL_dcolors, cudaStream_t s)
+                       float* dL_dopacity, float* dL_dcolors, const float* extra, const float* dL_dpix_extra,
+                       float* dL_dextra, cudaStream_t s)
 {
-    k_render_bwd<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib, contrib, dL_dpix,
-                                         dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
+    if (extra != nullptr)
+        k_render_bwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+                                                   contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, extra,
+                                                   dL_dpix_extra, dL_dextra);
+    else
+        k_render_bwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+                                                    contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, nullptr,
+                                                    nullptr, nullptr);
 }
 
 }  // namespace gsr

@@ -48,6 +48,7 @@ class _Gaussians(ctypes.Structure):
         ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p),
         ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
         ("cov3D_precomp", ctypes.c_void_p), ("scale_modifier", ctypes.c_float), ("_pad2", ctypes.c_int32),
+        ("extra_colors", ctypes.c_void_p),
     ]
 
 
@@ -63,7 +64,7 @@ class _Grads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "dL_dmeans2D", "dL_dconic", "dL_dopacity", "dL_dcolors", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
         "dL_dscales", "dL_drotations", "dL_dviewmatrix", "dL_dprojmatrix", "dL_dcampos")] + [
-        ("accumulate", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+        ("accumulate", ctypes.c_int32), ("_pad", ctypes.c_int32), ("dL_dextra", ctypes.c_void_p)]
 
 
 def _load():
@@ -86,13 +87,13 @@ def _load():
     lib.gsr_forward_preprocess.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, vp, sz, vp, sz,
                                            ctypes.POINTER(i32)]
     lib.gsr_forward_render.restype = ctypes.c_int
-    lib.gsr_forward_render.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, i64, vp, vp, sz, vp, vp]
+    lib.gsr_forward_render.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, i64, vp, vp, sz, vp, vp, vp]
     lib.gsr_backward.restype = ctypes.c_int
-    lib.gsr_backward.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, i64, vp, vp, vp, vp,
+    lib.gsr_backward.argtypes = [vp, ctypes.POINTER(_Gaussians), ctypes.POINTER(_Camera), vp, i64, vp, vp, vp, vp, vp,
                                  ctypes.POINTER(_Grads)]
     lib.gsr_mark_visible.restype = ctypes.c_int
     lib.gsr_mark_visible.argtypes = [vp, i32, vp, vp, vp, vp]
-    if lib.gsr_abi_version() != 2:
+    if lib.gsr_abi_version() != 3:
         raise ImportError("libgsrast_b200.so ABI version mismatch")
     return lib
 
@@ -129,17 +130,21 @@ def _snapshot(args, path):
 # ------------------------------------------------------------------------------------------------
 # Native calls
 # ------------------------------------------------------------------------------------------------
-def _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg):
+def _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
+             extra=None):
     P = means3D.shape[0]
     M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
     g = _Gaussians(P, int(rs.sh_degree), M, 0, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
-                   _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp), float(rs.scale_modifier), 0)
+                   _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp), float(rs.scale_modifier), 0, _ptr(extra))
     c = _Camera(int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy), _ptr(view), _ptr(proj),
                 _ptr(campos), _ptr(bg), int(bool(rs.prefiltered)), int(bool(rs.debug)))
     return g, c
 
 
-def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg):
+def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
+                    extra=None):
+    """Returns (R, color, radii, geom, binning, img); with `extra` ([P,3] colours) the 7th element is the
+    extra [3,H,W] image blended in the same pass."""
     dev = means3D.device
     P = means3D.shape[0]
     H, W = int(rs.image_height), int(rs.image_width)
@@ -147,25 +152,30 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
     u8 = dict(dtype=torch.uint8, device=dev)
     color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    has_extra = extra is not None and extra.numel() != 0
+    extra_img = torch.empty((3, H, W), dtype=torch.float32, device=dev) if has_extra else None
     if P == 0:
         color.zero_()
         e = torch.empty(0, **u8)
-        return 0, color, radii, e, e, e
+        return (0, color, radii, e, e, e) + ((torch.zeros_like(color),) if extra is not None else ())
     geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
     img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
-    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg)
+    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
+                    extra if has_extra else None)
     R = ctypes.c_int32(0)
     _check(_lib.gsr_forward_preprocess(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), geom.data_ptr(),
                                        geom.numel(), img.data_ptr(), img.numel(), ctypes.byref(R)))
     R = int(R.value)
     binning = torch.empty(_lib.gsr_binning_ws_bytes(R), **u8)
     _check(_lib.gsr_forward_render(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, geom.data_ptr(),
-                                   binning.data_ptr(), binning.numel(), img.data_ptr(), color.data_ptr()))
-    return R, color, radii, geom, binning, img
+                                   binning.data_ptr(), binning.numel(), img.data_ptr(), color.data_ptr(),
+                                   _ptr(extra_img)))
+    return (R, color, radii, geom, binning, img) + ((extra_img,) if has_extra else ())
 
 
 def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view,
-                     proj, campos, bg, radii, R, geom, binning, img, want_cam, targets=None):
+                     proj, campos, bg, radii, R, geom, binning, img, want_cam, targets=None, extra=None,
+                     grad_extra_img=None):
     """targets: optional dict of gradient accumulators (means3D, shs, opacities, scales, rotations) the
     kernels add into directly (gsr_grads.accumulate)."""
     dev = means3D.device
@@ -193,39 +203,46 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
         g_scales = torch.empty((P, 3), **f32) if has_sr else None
         g_rots = torch.empty((P, 4), **f32) if has_sr else None
     g_cam = torch.zeros(35, **f32) if want_cam else None
+    has_extra = extra is not None and extra.numel() != 0
+    g_extra = torch.zeros((P, 3), **f32) if has_extra else None
     if P == 0:
-        return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam
+        return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra
     stream = torch.cuda.current_stream(dev).cuda_stream
-    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg)
+    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
+                    extra if has_extra else None)
     gr = _Grads(g_means2D.data_ptr(), g_conic.data_ptr(), g_opacity.data_ptr(), g_colors.data_ptr(),
                 g_means3D.data_ptr(), _ptr(g_cov3D), _ptr(g_sh), _ptr(g_scales), _ptr(g_rots),
                 g_cam.data_ptr() if want_cam else None,
                 g_cam.data_ptr() + 64 if want_cam else None,
                 g_cam.data_ptr() + 128 if want_cam else None,
-                1 if targets else 0, 0)
+                1 if targets else 0, 0, _ptr(g_extra))
     _check(_lib.gsr_backward(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, _ptr(geom), _ptr(binning),
-                             _ptr(img), grad_color.data_ptr(), ctypes.byref(gr)))
-    return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam
+                             _ptr(img), grad_color.data_ptr(), _ptr(grad_extra_img) if has_extra else None,
+                             ctypes.byref(gr)))
+    return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra
 
 
 # ------------------------------------------------------------------------------------------------
 # Public API (same names and argument meaning as the reference)
 # ------------------------------------------------------------------------------------------------
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, grad_targets=None):
+                        raster_settings, grad_targets=None, extra_colors=None):
     """`grad_targets` (extension, optional): dict with fp32 contiguous accumulators for means3D, shs,
     opacities, scales, rotations.  The backward kernels then ADD this call's gradients straight into them
     (e.g. views of the map step's flat bucket) and autograd receives no gradient for those inputs — for
     the case where the rasterizer inputs ARE the optimised tensors."""
     rs = raster_settings
-    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos, grad_targets)
+    out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                    cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos, grad_targets,
+                                    extra_colors)
+    # reference contract: (color, radii); with extra_colors: (color, extra_image, radii)
+    return (out[0], out[1]) if extra_colors is None else (out[0], out[2], out[1])
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None):
+                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None, extra_colors=None):
         rs = raster_settings
         if grad_targets:
             if cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0:
@@ -246,9 +263,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         dev = means3D.device
         with torch.cuda.device(dev):
             t = [_prep(x, dev) for x in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                         viewmatrix, projmatrix, campos, rs.bg)]
-            means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_ = t
-            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_)
+                                         viewmatrix, projmatrix, campos, rs.bg, extra_colors)]
+            means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, extra_ = t
+            if extra_ is not None and (extra_.dim() != 2 or extra_.shape != (means3D.shape[0], 3)):
+                raise RuntimeError("extra_colors must have dimensions (num_points, 3)")
+            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_)
             if rs.debug:
                 try:
                     out = _forward_native(*args)
@@ -258,25 +277,35 @@ class _RasterizeGaussians(torch.autograd.Function):
                     raise
             else:
                 out = _forward_native(*args)
-        num_rendered, color, radii, geom, binning, img = out
+        num_rendered, color, radii, geom, binning, img = out[:6]
+        extra_img = out[6] if len(out) > 6 else None
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
+        ctx.has_extra = extra_img is not None
         ctx.save_for_backward(means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, radii,
-                              geom, binning, img)
+                              geom, binning, img, extra_ if ctx.has_extra else torch.empty(0))
         ctx.mark_non_differentiable(radii)
+        if ctx.has_extra:
+            return color, radii, extra_img
         return color, radii
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_radii):
+    def backward(ctx, grad_out_color, _grad_radii, grad_out_extra=None):
         rs = ctx.raster_settings
         (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, view, proj, campos, bg, radii,
-         geom, binning, img) = ctx.saved_tensors
+         geom, binning, img, extra) = ctx.saved_tensors
         dev = means3D.device
         want_cam = any(ctx.needs_input_grad[9:12])
         with torch.cuda.device(dev):
+            if grad_out_color is None:
+                grad_out_color = torch.zeros((3, int(rs.image_height), int(rs.image_width)), device=dev)
             grad = _prep(grad_out_color, dev)
+            grad_extra = None
+            if ctx.has_extra:
+                grad_extra = _prep(grad_out_extra, dev) if grad_out_extra is not None else torch.zeros_like(grad)
             args = (grad, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj,
-                    campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam, ctx.grad_targets)
+                    campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam, ctx.grad_targets,
+                    extra if ctx.has_extra else None, grad_extra)
             if rs.debug:
                 try:
                     res = _backward_native(*args)
@@ -286,7 +315,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     raise
             else:
                 res = _backward_native(*args)
-        g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam = res
+        g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra = res
         has_colors = colors_precomp is not None and colors_precomp.numel() != 0
         g_view = g_proj = g_campos = None
         if g_cam is not None:
@@ -295,11 +324,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_campos = g_cam[32:35].view_as(campos) if ctx.needs_input_grad[11] else None
         if ctx.grad_targets:   # already added into the accumulators by the kernels
             return (None, g_means2D, None, g_colors if has_colors else None, None, None, None, None,
-                    None, g_view, g_proj, g_campos, None)
+                    None, g_view, g_proj, g_campos, None, g_extra)
         if opacities.dim() == 1:
             g_opacity = g_opacity.view(-1)
         return (g_means3D, g_means2D, g_sh, g_colors if has_colors else None, g_opacity, g_scales, g_rots, g_cov3D,
-                None, g_view, g_proj, g_campos, None)
+                None, g_view, g_proj, g_campos, None, g_extra)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -340,7 +369,11 @@ class GaussianRasterizer(nn.Module):
             return present.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, grad_targets=None):
+                cov3D_precomp=None, grad_targets=None, extra_colors=None):
+        """Reference signature and return value (color[3,H,W], radii[P]).  Extensions (keyword-only in spirit):
+        `extra_colors` [P,3] -> returns (color, extra_image[3,H,W], radii): the extra colours are blended in the
+        same pass (the SLAM renderer's second, depth/silhouette call fused into the first);
+        `grad_targets`: see rasterize_gaussians."""
         rs = self.raster_settings
         if (shs is None) == (colors_precomp is None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
@@ -356,4 +389,4 @@ class GaussianRasterizer(nn.Module):
             empty if scales is None else scales,
             empty if rotations is None else rotations,
             empty if cov3D_precomp is None else cov3D_precomp,
-            rs, grad_targets)
+            rs, grad_targets, extra_colors)

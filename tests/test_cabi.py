@@ -21,17 +21,17 @@ def test_header_symbols_exported(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/gsrast_b200.h but not exported"
     lib.gsr_abi_version.restype = ctypes.c_int
-    assert lib.gsr_abi_version() == 2
+    assert lib.gsr_abi_version() == 3
 
 
 def test_struct_mirrors_match_c_layout(built_lib):
     import diff_gaussian_rasterization as dgr
     # 4 x int32 + 7 pointers + float + int32
-    assert ctypes.sizeof(dgr._Gaussians) == 16 + 7 * 8 + 8
+    assert ctypes.sizeof(dgr._Gaussians) == 16 + 7 * 8 + 8 + 8 and dgr._Gaussians.extra_colors.offset == 80
     assert dgr._Gaussians.means3D.offset == 16 and dgr._Gaussians.scale_modifier.offset == 72
     assert ctypes.sizeof(dgr._Camera) == 16 + 4 * 8 + 8
     assert dgr._Camera.viewmatrix.offset == 16 and dgr._Camera.prefiltered.offset == 48
-    assert ctypes.sizeof(dgr._Grads) == 12 * 8 + 8 and dgr._Grads.accumulate.offset == 96
+    assert ctypes.sizeof(dgr._Grads) == 12 * 8 + 8 + 8 and dgr._Grads.accumulate.offset == 96 and dgr._Grads.dL_dextra.offset == 104
 
 
 def test_python_surface_matches_reference(built_lib):

@@ -298,3 +298,69 @@ def test_grad_targets_accumulate(dgr):
     a, b = run(False), run(True)
     for k in names:
         assert rel_err(b[k], a[k]) < 1e-5, k
+
+
+def _slam_case(dev, P=30000, W=320, H=240, deg=0, seed=51):
+    import gsr_synth as S
+    from tests.util import scene_on
+    gs, _, dL, bg = scene_on(dev, P, W, H, seed, deg)
+    g = torch.Generator().manual_seed(seed)
+    dL2 = torch.randn(3, H, W, generator=g).to(dev)
+    w2c = S.look_at_w2c((0.3, -0.1, 0.2), (0.0, 0.0, 4.0)).to(dev)
+    return gs, dL, dL2, torch.tensor([0.0, 0.0, 0.0], device=dev), w2c, W, H
+
+
+def _slam_backward(rasterize, settings_cls, gs, dL, dL2, bg, w2c, W, H, deg=0):
+    from tests import slam_glue
+    dev = w2c.device
+    p = {k: v.clone().requires_grad_(True) for k, v in gs.items()}
+    pose = w2c.clone().requires_grad_(True)
+    rs = slam_glue.settings(settings_cls, W, H, bg, deg, dev)
+    rgb, depth, radii, m2 = slam_glue.render_two_pass(rasterize, rs, p, pose)
+    ((rgb * dL).sum() + (depth * dL2).sum()).backward()
+    g = {k: v.grad for k, v in p.items()}
+    g["pose"], g["means2D"] = pose.grad, m2.grad
+    return rgb.detach(), depth.detach(), radii, g
+
+
+def test_slam_render_pattern_vs_reference(dgr, ref):
+    """The reference renderer's call pattern (two passes, shared means2D leaf, python-side pose transform)
+    through the drop-in and through the compiled reference: images, all parameter gradients, the pose
+    gradient and the accumulated viewspace gradient agree."""
+    from collections import namedtuple
+    from tests.util import rel_err
+    dev = torch.device("cuda:0")
+    gs, dL, dL2, bg, w2c, W, H = _slam_case(dev)
+    RS = namedtuple("RS", dgr.GaussianRasterizationSettings._fields)
+    a = _slam_backward(_ours(dgr), dgr.GaussianRasterizationSettings, gs, dL, dL2, bg, w2c, W, H)
+    b = _slam_backward(_theirs(ref), RS, gs, dL, dL2, bg, w2c, W, H)
+    assert torch.equal(a[2], b[2])
+    assert rel_err(a[0], b[0]) < TOL and rel_err(a[1], b[1]) < TOL
+    for k in b[3]:
+        assert rel_err(a[3][k], b[3][k]) < TOL, (k, rel_err(a[3][k], b[3][k]))
+
+
+@pytest.mark.parametrize("deg", [0, 2])
+def test_fused_rgb_depth_equals_two_passes(dgr, deg):
+    """Extension: one call with extra_colors == the two-pass render, images and gradients."""
+    from tests import slam_glue
+    from tests.util import rel_err
+    dev = torch.device("cuda:0")
+    gs, dL, dL2, bg, w2c, W, H = _slam_case(dev, deg=deg, seed=52)
+    bg = torch.tensor([0.2, 0.4, 0.1], device=dev)
+    a = _slam_backward(_ours(dgr), dgr.GaussianRasterizationSettings, gs, dL, dL2, bg, w2c, W, H, deg)
+    p = {k: v.clone().requires_grad_(True) for k, v in gs.items()}
+    pose = w2c.clone().requires_grad_(True)
+    rs = slam_glue.settings(dgr.GaussianRasterizationSettings, W, H, bg, deg, dev)
+    means_cam = slam_glue.camera_frame(p, pose)
+    m2 = torch.zeros_like(means_cam, requires_grad=True)
+    rgb, depth, radii = dgr.GaussianRasterizer(rs)(means3D=means_cam, means2D=m2, opacities=p["opacities"], shs=p["shs"],
+                                                   scales=p["scales"], rotations=p["rotations"],
+                                                   extra_colors=slam_glue.depth_silhouette(means_cam))
+    ((rgb * dL).sum() + (depth * dL2).sum()).backward()
+    assert torch.equal(radii, a[2])
+    assert rel_err(rgb, a[0]) < 1e-6 and rel_err(depth, a[1]) < 1e-6
+    g = {k: v.grad for k, v in p.items()}
+    g["pose"], g["means2D"] = pose.grad, m2.grad
+    for k in g:
+        assert rel_err(g[k], a[3][k]) < 2e-5, (k, rel_err(g[k], a[3][k]))
