@@ -15,7 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libgsrast_b200.so")
-SOURCES = ["preprocess.cu", "binning.cu", "render.cu", "c_api.cu"]
+SOURCES = ["preprocess.cu", "preprocess_bwd.cu", "binning.cu", "render.cu", "c_api.cu"]
+# per-file extra flags.  (--use_fast_math on preprocess_bwd.cu — legal there, nothing in the backward feeds an
+# integer output — was measured SLOWER on B200: 74 vs 64 registers, 106 vs 95 us; so everything uses nvcc defaults.)
+EXTRA_FLAGS = {"preprocess_bwd.cu": ["--use_fast_math"] if os.environ.get("GSR_FAST_BWD") else []}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # nvcc floating-point defaults on purpose (-fmad=true, IEEE div/sqrt, no fast-math): the integer
@@ -59,7 +62,8 @@ def build(force=False, verbose=False, ptxas_info=False, defines=(), out=None):
     for s in SOURCES:
         o = os.path.join(objdir, s + ".o")
         objs.append(o)
-        jobs.append([NVCC, "-c", os.path.join(CSRC, s), "-o", o] + ARCH + CFLAGS + extra + ["-D" + d for d in defines])
+        jobs.append([NVCC, "-c", os.path.join(CSRC, s), "-o", o] + ARCH + CFLAGS + extra + EXTRA_FLAGS.get(s, [])
+                    + ["-D" + d for d in defines])
     with ThreadPoolExecutor(len(jobs)) as ex:
         list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))
     _run([NVCC, "-shared", "-o", so] + objs + ARCH + ["-cudart", "shared", "-Xcompiler", "-fPIC"], verbose)

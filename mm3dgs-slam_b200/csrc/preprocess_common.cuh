@@ -1,0 +1,65 @@
+// preprocess_common.cuh — block-wide staging helpers shared by the per-Gaussian kernels.
+#pragma once
+#include "gsr_internal.cuh"
+#include "gsr_math.cuh"
+#include <stdio.h>
+
+namespace gsr {
+
+
+constexpr int kPB = 256;  // Gaussians (threads) per block
+
+__device__ __forceinline__ float4 ld_stream4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream1(const float* p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// Copy n contiguous floats global -> shared with the widest aligned transactions available.
+__device__ __forceinline__ void stage_in(const float* __restrict__ src, float* dst, int n, int tid)
+{
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < n4; i += kPB) d4[i] = ld_stream4(s4 + i);
+        for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = ld_stream1(src + i);
+    } else {
+        for (int i = tid; i < n; i += kPB) dst[i] = ld_stream1(src + i);
+    }
+}
+// Copy n contiguous floats shared -> global; ACC: add `old` (the accumulator's previous contents, staged into
+// shared memory at kernel start so that the read overlaps the math instead of sitting in front of the store).
+template <bool ACC>
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, const float* old, int n, int tid)
+{
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int n4 = n >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        const float4* o4 = reinterpret_cast<const float4*>(old);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < n4; i += kPB) {
+            float4 v = s4[i];
+            if (ACC) {
+                const float4 o = o4[i];
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            d4[i] = v;
+        }
+        for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = ACC ? old[i] + src[i] : src[i];
+    } else {
+        for (int i = tid; i < n; i += kPB) dst[i] = ACC ? old[i] + src[i] : src[i];
+    }
+}
+
+
+}  // namespace gsr
