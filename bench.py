@@ -389,8 +389,13 @@ def main():
     dom = max(stages, key=lambda k: stages[k]["ms"])
     line["stages"] = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 3), "gbs": round(v["gbs"], 1)}
                       for k, v in stages.items()}
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom)
+    except Exception:
+        pass
     line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                         "alg_bytes_per_launch": stages[dom]["alg_bytes"], "ms_per_launch": stages[dom]["ms"],
                         "call_alg_bytes": sum(sb.values()), "call_ms_sum_of_stages": total_ms,
                         "call_frac": sum(sb.values()) / (total_ms * 1e-3) / 1e9 / peak}

@@ -364,3 +364,67 @@ def test_fused_rgb_depth_equals_two_passes(dgr, deg):
     g["pose"], g["means2D"] = pose.grad, m2.grad
     for k in g:
         assert rel_err(g[k], a[3][k]) < 2e-5, (k, rel_err(g[k], a[3][k]))
+
+
+@pytest.mark.parametrize("P,W,H,deg,seed", [
+    (150000, 1920, 1080, 0, 61),   # 8160 tiles: partition with 8 warps/CTA and ~160 KB of per-warp counters
+    (60000, 2560, 1440, 1, 62),    # 14400 tiles: 4 warps/CTA
+    (3000, 16, 16, 0, 63),         # a single tile
+    (257, 33, 17, 2, 64),          # ragged everything, P just over one block
+])
+def test_image_size_extremes_vs_reference(dgr, ref, P, W, H, deg, seed):
+    from tests import ws_decode
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    gs, cam, dL, bg = scene_on(dev, P, W, H, seed, deg)
+    rs = settings_for(dgr, cam, bg, deg, dev)
+    c1, r1, g1 = _run(_ours(dgr), gs, rs, dL, "sh")
+    c2, r2, g2 = _run(_theirs(ref), gs, rs, dL, "sh")
+    assert torch.equal(r1, r2)
+    assert rel_err(c1, c2) < TOL
+    for k in g2:
+        assert rel_err(g1[k], g2[k]) < TOL, (k, rel_err(g1[k], g2[k]))
+    # and the instance lists, bit for bit
+    with torch.no_grad():
+        R, _, radii, geom, binning, img = dgr._forward_native(
+            gs["means3D"], gs["shs"], None, gs["opacities"], gs["scales"], gs["rotations"], None, rs,
+            rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+        f = ref.forward(gs["means3D"], gs["opacities"], rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg, W, H,
+                        cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], deg)
+    torch.cuda.synchronize()
+    assert R == f["num_rendered"]
+    mg, mi = ws_decode.decode_geom(geom, P, W, H), ws_decode.decode_img(img, W, H)
+    mb, rb = ws_decode.decode_binning(binning, R, mg, mi), ref.decode_binning(f["binning"], R)
+    assert torch.equal(mb["point_list"], rb["point_list"]) and torch.equal(mb["keys"], rb["keys"])
+    assert torch.equal(mi["n_contrib"], ref.decode_img(f["img"], W, H)["n_contrib"])
+
+
+def test_huge_splats_and_duplicates(dgr, ref):
+    """Splats covering the whole tile grid, many exactly equal depths (ties must keep index order) and
+    duplicated Gaussians."""
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 4000, 320, 240
+    gs, cam, dL, bg = scene_on(dev, P, W, H, 71, 0)
+    gs["scales"][:200] *= 400.0                       # whole-screen splats
+    gs["means3D"][200:1200, 2] = 2.5                   # a thousand identical depths
+    gs["means3D"][1200:1400] = gs["means3D"][1400:1600]   # exact duplicates
+    gs["scales"][1200:1400] = gs["scales"][1400:1600]
+    rs = settings_for(dgr, cam, bg, 0, dev)
+    c1, r1, g1 = _run(_ours(dgr), gs, rs, dL, "sh")
+    c2, r2, g2 = _run(_theirs(ref), gs, rs, dL, "sh")
+    assert torch.equal(r1, r2)
+    assert rel_err(c1, c2) < TOL
+    for k in g2:
+        assert rel_err(g1[k], g2[k]) < TOL, (k, rel_err(g1[k], g2[k]))
+    with torch.no_grad():
+        R, _, _, geom, binning, img = dgr._forward_native(
+            gs["means3D"], gs["shs"], None, gs["opacities"], gs["scales"], gs["rotations"], None, rs,
+            rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+        f = ref.forward(gs["means3D"], gs["opacities"], rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg, W, H,
+                        cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], 0)
+    from tests import ws_decode
+    torch.cuda.synchronize()
+    mg, mi = ws_decode.decode_geom(geom, P, W, H), ws_decode.decode_img(img, W, H)
+    mb, rb = ws_decode.decode_binning(binning, R, mg, mi), ref.decode_binning(f["binning"], R)
+    assert R == f["num_rendered"] and torch.equal(mb["point_list"], rb["point_list"])
