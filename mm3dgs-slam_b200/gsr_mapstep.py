@@ -128,10 +128,24 @@ class ShardedMapStep:
     def my_keyframes(self, keyframes: Sequence):
         return [keyframes[i] for i in shard_keyframes(len(keyframes), self.rank, self.world)]
 
-    def step(self, keyframes: Sequence):
-        """Sum of per-keyframe gradients in self.bucket.flat on every rank. Returns the local losses."""
+    def step(self, keyframes: Sequence, params: Optional[Dict[str, torch.Tensor]] = None):
+        """Sum of per-keyframe gradients in self.bucket.flat on every rank. Returns the local losses.
+        `params`: optional replacement parameter tensors for this step (same shapes) — used when the caller
+        double-buffers parameter uploads; only valid with direct_targets (gradients do not go through .grad)."""
+        if params is not None and not self.direct_targets:
+            raise ValueError("per-step params need direct_targets=True")
+        saved = self.params
+        if params is not None:
+            self.params = params
+        try:
+            return self._step(keyframes)
+        finally:
+            self.params = saved
+
+    def _step(self, keyframes: Sequence):
         self.bucket.zero_()
-        self.bucket.attach()
+        if not self.direct_targets:
+            self.bucket.attach()
         mine = self.my_keyframes(keyframes)
         if self.forward_fn is not None:
             outs = self._forwards(mine)
