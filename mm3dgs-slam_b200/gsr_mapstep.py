@@ -113,7 +113,7 @@ class ShardedMapStep:
                 return [self.forward_fn(self.params, kf, self._targets(0)) for kf in mine]
             return [self.forward_fn(self.params, kf) for kf in mine]
         main = torch.cuda.current_stream()
-        for flat in self.aux_flat:
+        for flat in self.aux_flat[: max(0, min(self.nstreams, len(mine)) - 1)]:
             flat.zero_()
         for st in self.streams:
             st.wait_stream(main)
@@ -157,7 +157,7 @@ class ShardedMapStep:
                     main.wait_stream(st)
                 for o, _ in outs:
                     o.record_stream(main)
-            for flat in self.aux_flat:
+            for flat in self.aux_flat[: max(0, min(self.nstreams, len(mine)) - 1)]:   # only the streams used
                 self.bucket.flat.add_(flat)
             losses = [o.detach() for o, _ in outs]
         else:
