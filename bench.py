@@ -254,18 +254,23 @@ def main():
         from gsr_mapstep import ShardedMapStep
         kfs = settings_list(dgr.GaussianRasterizationSettings, cams, bg, args.sh_degree, device)
 
-        def forward_fn(p, rs, targets=None):
+        def prepare_fn(p, rs):   # phase 1 of every keyframe is enqueued before the first host hand-off
+            return dgr.prepare_forward(p["means3D"], p["opacities"], rs, shs=p["shs"], scales=p["scales"],
+                                       rotations=p["rotations"])
+
+        def forward_fn(p, rs, targets=None, handle=None):
             m2 = torch.zeros(P, 3, device=device, requires_grad=True)
             color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"],
                                                   shs=p["shs"], scales=p["scales"], rotations=p["rotations"],
-                                                  grad_targets=targets)
+                                                  grad_targets=targets, prepared=handle)
             return color, dL          # back-propagated with the fixed dL/dpix by ShardedMapStep.step
 
         # the rasterizer inputs ARE the optimised tensors here, so the backward kernels add straight into the
         # flat gradient bucket instead of returning tensors for autograd to accumulate;
         # consecutive keyframes alternate between two CUDA streams (binning of one overlaps blending of another)
         stepper = ShardedMapStep(params, forward_fn=forward_fn, streams=int(os.environ.get("GSR_BENCH_STREAMS", "4")),
-                                 direct_targets=not os.environ.get("GSR_BENCH_NO_TARGETS"))
+                                 direct_targets=not os.environ.get("GSR_BENCH_NO_TARGETS"),
+                                 prepare_fn=None if os.environ.get("GSR_BENCH_NO_PREPARE") else prepare_fn)
         step = lambda: stepper.step(kfs)  # noqa: E731
         launch_count = dgr._lib.gsr_launch_count
         launch_count.restype = ctypes.c_longlong

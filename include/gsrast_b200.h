@@ -128,7 +128,9 @@ size_t gsr_binning_ws_bytes(int64_t R);
  * instance count R, and the depth sort of the Gaussians.  Writes radii[P].  If num_rendered is not
  * NULL the call waits (on an event recorded right after the projection kernel, not on the whole
  * stream) and stores R there (host memory) so the caller can size the binning workspace — the one
- * host hand-off the reference also has (rasterizer_impl.cu:280-281). */
+ * host hand-off the reference also has (rasterizer_impl.cu:280-281).  With num_rendered == NULL nothing
+ * is waited for: the caller fetches R itself later from geom_ws + gsr_geom_layout.counters (e.g. with an
+ * asynchronous copy + event), which lets it enqueue phase 1 of many frames before the first hand-off. */
 int gsr_forward_preprocess(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                            int32_t* radii, void* geom_ws, size_t geom_ws_bytes,
                            void* img_ws, size_t img_ws_bytes, int32_t* num_rendered);
@@ -168,6 +170,7 @@ typedef struct gsr_geom_layout {
     size_t rects;      /* ushort4[P]: tile rectangle {x0,y0,x1,y1}, empty for culled Gaussians */
     size_t depth_keys; /* uint32[P]: float bits of the view depth, 0xFFFFFFFF for culled Gaussians */
     size_t sorted_ids; /* uint32[P]: Gaussian ids in (depth, index) order, culled last */
+    size_t counters;   /* uint32[>=1]: [0] = R, the number of tile instances (valid after gsr_forward_preprocess) */
     size_t total;
 } gsr_geom_layout;
 typedef struct gsr_img_layout { size_t final_T, n_contrib, ranges, total; } gsr_img_layout;

@@ -211,6 +211,7 @@ void gsr_geom_layout_of(int32_t P, int32_t W, int32_t H, gsr_geom_layout* o)
     o->rects = (size_t)w.rects;
     o->depth_keys = (size_t)w.depth_keys;
     o->sorted_ids = (size_t)w.sort.vals_a;
+    o->counters = (size_t)w.counters;
     o->total = w.total;
 }
 void gsr_img_layout_of(int32_t W, int32_t H, gsr_img_layout* o)

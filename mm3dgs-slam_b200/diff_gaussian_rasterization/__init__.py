@@ -31,7 +31,7 @@ from typing import NamedTuple
 import torch
 import torch.nn as nn
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "prepare_forward"]
 
 # ------------------------------------------------------------------------------------------------
 # Library loading
@@ -141,8 +141,68 @@ def _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     return g, c
 
 
+class _GeomLayout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "rects", "depth_keys", "sorted_ids", "counters", "total")]
+
+
+_pinned_pool = {}
+
+
+def _pinned_slot(dev):
+    """Small ring of pinned int32 slots per device (cudaHostAlloc is far too slow to call per frame)."""
+    ring = _pinned_pool.setdefault(dev.index, {"buf": torch.empty(256, dtype=torch.int32).pin_memory(), "i": 0})
+    ring["i"] = (ring["i"] + 1) % 256
+    return ring["buf"][ring["i"]: ring["i"] + 1]
+
+
+class PreparedFrame:
+    """Phase 1 of a forward (projection + depth sort) already enqueued; see prepare_forward()."""
+    __slots__ = ("tensors", "rs", "radii", "geom", "img", "r_host", "event", "stream", "g", "c")
+
+
+def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precomp=None, scales=None, rotations=None,
+                    cov3D_precomp=None, extra_colors=None):
+    """Extension.  Enqueue phase 1 of a forward (projection, tile rectangles, instance count R, depth sort)
+    without waiting for R, and return a handle to pass as `prepared=` to GaussianRasterizer.forward with the
+    SAME tensors and settings.  Issuing phase 1 of several frames before the first forward() means every
+    frame's R is already on the host when its forward() needs it — the host never stalls on the hand-off."""
+    rs = raster_settings
+    if not means3D.is_cuda:
+        raise RuntimeError("gsrast_b200: tensors must live on a CUDA device (there is no CPU path)")
+    dev = means3D.device
+    e = torch.Tensor([])
+    with torch.cuda.device(dev):
+        t = [_prep(x if x is not None else e, dev) for x in (means3D, shs, colors_precomp, opacities, scales, rotations,
+                                                             cov3D_precomp, rs.viewmatrix, rs.projmatrix, rs.campos,
+                                                             rs.bg)]
+        extra = _prep(extra_colors, dev)
+        P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        pf = PreparedFrame()
+        pf.tensors, pf.rs = tuple(t) + (extra,), rs
+        pf.stream = torch.cuda.current_stream(dev)
+        pf.radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        if P == 0:
+            pf.geom = pf.img = pf.r_host = pf.event = None
+            return pf
+        u8 = dict(dtype=torch.uint8, device=dev)
+        pf.geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
+        pf.img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
+        pf.g, pf.c = _structs(*t[:7], rs, *t[7:11], extra if (extra is not None and extra.numel()) else None)
+        _check(_lib.gsr_forward_preprocess(pf.stream.cuda_stream, ctypes.byref(pf.g), ctypes.byref(pf.c),
+                                           pf.radii.data_ptr(), pf.geom.data_ptr(), pf.geom.numel(), pf.img.data_ptr(),
+                                           pf.img.numel(), None))
+        lay = _GeomLayout()
+        _lib.gsr_geom_layout_of(ctypes.c_int32(P), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(lay))
+        pf.r_host = _pinned_slot(dev)
+        pf.r_host.copy_(pf.geom[lay.counters: lay.counters + 4].view(torch.int32), non_blocking=True)
+        pf.event = torch.cuda.Event()
+        pf.event.record(pf.stream)
+    return pf
+
+
 def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
-                    extra=None):
+                    extra=None, prepared=None):
     """Returns (R, color, radii, geom, binning, img); with `extra` ([P,3] colours) the 7th element is the
     extra [3,H,W] image blended in the same pass."""
     dev = means3D.device
@@ -158,14 +218,26 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
         color.zero_()
         e = torch.empty(0, **u8)
         return (0, color, radii, e, e, e) + ((torch.zeros_like(color),) if extra is not None else ())
-    geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
-    img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
-    g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
-                    extra if has_extra else None)
-    R = ctypes.c_int32(0)
-    _check(_lib.gsr_forward_preprocess(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), geom.data_ptr(),
-                                       geom.numel(), img.data_ptr(), img.numel(), ctypes.byref(R)))
-    R = int(R.value)
+    if prepared is not None:
+        if prepared.tensors[0].data_ptr() != means3D.data_ptr() or prepared.radii.shape[0] != P or prepared.rs is not rs:
+            raise RuntimeError("gsrast_b200: `prepared` was made for different inputs / settings")
+        radii, geom, img, g, c = prepared.radii, prepared.geom, prepared.img, prepared.g, prepared.c
+        cur = torch.cuda.current_stream(dev)
+        if cur != prepared.stream:
+            cur.wait_stream(prepared.stream)
+        prepared.event.synchronize()
+        R = int(prepared.r_host.item())
+        if R < 0:
+            raise RuntimeError("gsrast_b200: more than 2^31-1 tile instances")
+    else:
+        geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
+        img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
+        g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos,
+                        bg, extra if has_extra else None)
+        R = ctypes.c_int32(0)
+        _check(_lib.gsr_forward_preprocess(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), geom.data_ptr(),
+                                           geom.numel(), img.data_ptr(), img.numel(), ctypes.byref(R)))
+        R = int(R.value)
     binning = torch.empty(_lib.gsr_binning_ws_bytes(R), **u8)
     _check(_lib.gsr_forward_render(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, geom.data_ptr(),
                                    binning.data_ptr(), binning.numel(), img.data_ptr(), color.data_ptr(),
@@ -226,7 +298,7 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
 # Public API (same names and argument meaning as the reference)
 # ------------------------------------------------------------------------------------------------
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, grad_targets=None, extra_colors=None):
+                        raster_settings, grad_targets=None, extra_colors=None, prepared=None):
     """`grad_targets` (extension, optional): dict with fp32 contiguous accumulators for means3D, shs,
     opacities, scales, rotations.  The backward kernels then ADD this call's gradients straight into them
     (e.g. views of the map step's flat bucket) and autograd receives no gradient for those inputs — for
@@ -234,7 +306,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     rs = raster_settings
     out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos, grad_targets,
-                                    extra_colors)
+                                    extra_colors, prepared)
     # reference contract: (color, radii); with extra_colors: (color, extra_image, radii)
     return (out[0], out[1]) if extra_colors is None else (out[0], out[2], out[1])
 
@@ -242,7 +314,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None, extra_colors=None):
+                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None, extra_colors=None, prepared=None):
         rs = raster_settings
         if grad_targets:
             if cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0:
@@ -267,7 +339,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, extra_ = t
             if extra_ is not None and (extra_.dim() != 2 or extra_.shape != (means3D.shape[0], 3)):
                 raise RuntimeError("extra_colors must have dimensions (num_points, 3)")
-            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_)
+            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_, prepared)
             if rs.debug:
                 try:
                     out = _forward_native(*args)
@@ -324,11 +396,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_campos = g_cam[32:35].view_as(campos) if ctx.needs_input_grad[11] else None
         if ctx.grad_targets:   # already added into the accumulators by the kernels
             return (None, g_means2D, None, g_colors if has_colors else None, None, None, None, None,
-                    None, g_view, g_proj, g_campos, None, g_extra)
+                    None, g_view, g_proj, g_campos, None, g_extra, None)
         if opacities.dim() == 1:
             g_opacity = g_opacity.view(-1)
         return (g_means3D, g_means2D, g_sh, g_colors if has_colors else None, g_opacity, g_scales, g_rots, g_cov3D,
-                None, g_view, g_proj, g_campos, None, g_extra)
+                None, g_view, g_proj, g_campos, None, g_extra, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -369,11 +441,11 @@ class GaussianRasterizer(nn.Module):
             return present.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, grad_targets=None, extra_colors=None):
+                cov3D_precomp=None, grad_targets=None, extra_colors=None, prepared=None):
         """Reference signature and return value (color[3,H,W], radii[P]).  Extensions (keyword-only in spirit):
         `extra_colors` [P,3] -> returns (color, extra_image[3,H,W], radii): the extra colours are blended in the
         same pass (the SLAM renderer's second, depth/silhouette call fused into the first);
-        `grad_targets`: see rasterize_gaussians."""
+        `grad_targets`: see rasterize_gaussians; `prepared`: handle from prepare_forward()."""
         rs = self.raster_settings
         if (shs is None) == (colors_precomp is None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
@@ -389,4 +461,4 @@ class GaussianRasterizer(nn.Module):
             empty if scales is None else scales,
             empty if rotations is None else rotations,
             empty if cov3D_precomp is None else cov3D_precomp,
-            rs, grad_targets, extra_colors)
+            rs, grad_targets, extra_colors, prepared)

@@ -72,7 +72,7 @@ class ShardedMapStep:
 
     def __init__(self, params: Dict[str, torch.Tensor], frame_fn: Optional[Callable] = None,
                  group: Optional[dist.ProcessGroup] = None, forward_fn: Optional[Callable] = None,
-                 streams: int = 1, direct_targets: bool = False):
+                 streams: int = 1, direct_targets: bool = False, prepare_fn: Optional[Callable] = None):
         """streams > 1 (forward_fn mode, CUDA only): consecutive keyframes alternate between `streams` CUDA
         streams, so the latency-bound binning kernels of one frame overlap the blend kernels of another.
         direct_targets: forward_fn receives a third argument, a dict of gradient accumulators (views of a flat
@@ -84,6 +84,10 @@ class ShardedMapStep:
         self.bucket = GradBucket(params)
         self.frame_fn = frame_fn
         self.forward_fn = forward_fn
+        # prepare_fn(params, keyframe) -> handle: enqueues the part of the forward that precedes its host
+        # hand-off (diff_gaussian_rasterization.prepare_forward); it is issued for ALL of the rank's keyframes
+        # before the first forward_fn call, which then receives the handle as its last argument.
+        self.prepare_fn = prepare_fn
         self.group = group
         self.direct_targets = direct_targets
         first = next(iter(params.values()))
@@ -107,22 +111,31 @@ class ShardedMapStep:
             return None
         return self.bucket.views if i == 0 else self.aux_views[i - 1]
 
+    def _call_forward(self, kf, i, handle):
+        args = (self.params, kf) + ((self._targets(i),) if self.direct_targets else ())
+        if self.prepare_fn is not None:
+            args = args + (handle,)
+        return self.forward_fn(*args)
+
     def _forwards(self, mine):
-        if self.nstreams == 1:
-            if self.direct_targets:
-                return [self.forward_fn(self.params, kf, self._targets(0)) for kf in mine]
-            return [self.forward_fn(self.params, kf) for kf in mine]
+        n = self.nstreams
+        if n == 1:
+            handles = [self.prepare_fn(self.params, kf) for kf in mine] if self.prepare_fn else [None] * len(mine)
+            return [self._call_forward(kf, 0, h) for kf, h in zip(mine, handles)]
         main = torch.cuda.current_stream()
-        for flat in self.aux_flat[: max(0, min(self.nstreams, len(mine)) - 1)]:
+        for flat in self.aux_flat[: max(0, min(n, len(mine)) - 1)]:
             flat.zero_()
         for st in self.streams:
             st.wait_stream(main)
+        handles = [None] * len(mine)
+        if self.prepare_fn is not None:
+            for j, kf in enumerate(mine):
+                with torch.cuda.stream(self.streams[j % n]):
+                    handles[j] = self.prepare_fn(self.params, kf)
         outs = []
         for j, kf in enumerate(mine):
-            i = j % self.nstreams
-            with torch.cuda.stream(self.streams[i]):
-                outs.append(self.forward_fn(self.params, kf, self._targets(i)) if self.direct_targets
-                            else self.forward_fn(self.params, kf))
+            with torch.cuda.stream(self.streams[j % n]):
+                outs.append(self._call_forward(kf, j % n, handles[j]))
         return outs
 
     def my_keyframes(self, keyframes: Sequence):

@@ -428,3 +428,30 @@ def test_huge_splats_and_duplicates(dgr, ref):
     mg, mi = ws_decode.decode_geom(geom, P, W, H), ws_decode.decode_img(img, W, H)
     mb, rb = ws_decode.decode_binning(binning, R, mg, mi), ref.decode_binning(f["binning"], R)
     assert R == f["num_rendered"] and torch.equal(mb["point_list"], rb["point_list"])
+
+
+def test_prepared_forward_equals_plain(dgr):
+    """prepare_forward() + forward(prepared=...) == plain forward, for several frames prepared up front."""
+    import gsr_synth as S
+    from tests.util import scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 20000, 160, 120
+    gs, _, dL, bg = scene_on(dev, P, W, H, 81, 0)
+    cams = S.orbit_cameras(W, H, 3, (0.0, 0.0, 4.0), 0.4)
+    rss = [settings_for(dgr, c, bg, 0, dev) for c in cams]
+    kw = dict(shs=gs["shs"], scales=gs["scales"], rotations=gs["rotations"])
+    handles = [dgr.prepare_forward(gs["means3D"], gs["opacities"], rs, **kw) for rs in rss]
+    for rs, h in zip(rss, handles):
+        m = gs["means3D"].detach().clone().requires_grad_(True)
+        a, ra = dgr.GaussianRasterizer(rs)(means3D=m, means2D=torch.zeros(P, 3, device=dev), opacities=gs["opacities"], **kw)
+        (a * dL).sum().backward()
+        m2 = gs["means3D"].requires_grad_(True)
+        m2.grad = None
+        b, rb = dgr.GaussianRasterizer(rs)(means3D=m2, means2D=torch.zeros(P, 3, device=dev), opacities=gs["opacities"],
+                                           prepared=h, **kw)
+        (b * dL).sum().backward()
+        assert torch.equal(ra, rb) and torch.equal(a, b)
+        assert torch.allclose(m.grad, m2.grad, rtol=1e-4, atol=1e-6 * float(m.grad.abs().max()))
+    with pytest.raises(RuntimeError):
+        dgr.GaussianRasterizer(rss[0])(means3D=gs["means3D"].detach().clone(), means2D=None, opacities=gs["opacities"],
+                                       prepared=handles[1], **kw)

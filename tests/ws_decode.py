@@ -8,7 +8,7 @@ import diff_gaussian_rasterization as dgr
 
 
 class _GeomLayout(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "rects", "depth_keys", "sorted_ids", "total")]
+    _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "rects", "depth_keys", "sorted_ids", "counters", "total")]
 
 
 class _ImgLayout(ctypes.Structure):
