@@ -256,8 +256,11 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+#ifndef GSR_BWD_MIN_CTAS
+#define GSR_BWD_MIN_CTAS 5
+#endif
 template <bool EXTRA>
-__global__ void __launch_bounds__(256) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(256, EXTRA ? 4 : GSR_BWD_MIN_CTAS) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
                                                     const uint32_t* __restrict__ order,
                                                     const uint32_t* __restrict__ point_list,
                                                     const float4* __restrict__ rec, const float* __restrict__ bg,
