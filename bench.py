@@ -200,8 +200,22 @@ def measure_m2(rasterize, settings_cls, params, dL, device, args, fused=None, it
                                   rotations=p["rotations"], extra_colors=slam_glue.depth_silhouette(mc))
         ((rgb * dL).sum() + (depth * dL).sum()).backward()
 
+    def native():   # pose as view/proj matrices (library camera gradients), depth colours generated in the library
+        import diff_gaussian_rasterization as dgr_
+        pose = w2c.clone().requires_grad_(True)
+        view = pose.t()
+        proj = view @ S.projection_matrix(*S.intrinsics(W, H), W, H).t().to(device)
+        rs2 = settings_cls(image_height=H, image_width=W, tanfovx=rs.tanfovx, tanfovy=rs.tanfovy, bg=bg,
+                           scale_modifier=1.0, viewmatrix=view, projmatrix=proj, sh_degree=args.sh_degree,
+                           campos=torch.linalg.inv(view)[3, :3], prefiltered=False, debug=False)
+        m2 = torch.zeros(P, 3, device=device, requires_grad=True)
+        rgb, depth, _ = fused(rs2)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"], shs=p["shs"],
+                                   scales=p["scales"], rotations=p["rotations"], extra_colors=dgr_.DEPTH_SILHOUETTE)
+        ((rgb * dL).sum() + (depth * dL).sum()).backward()
+
     out = {}
-    for name, fn in (("two_pass", two_pass),) + ((("fused_rgbd", one_pass),) if fused is not None else ()):
+    for name, fn in (("two_pass", two_pass),) + ((("fused_rgbd", one_pass), ("fused_native_pose", native))
+                                                 if fused is not None else ()):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()

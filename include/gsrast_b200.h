@@ -68,7 +68,10 @@ typedef struct gsr_gaussians {
     const float* rotations;    /* [P,4] (r,x,y,z; NOT normalised by the kernel) or NULL */
     const float* cov3D_precomp; /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
     float scale_modifier;
-    int32_t _pad2;
+    int32_t extra_mode;        /* 0: extra colours (if any) come from extra_colors; 1: the library GENERATES the SLAM
+                                * depth/silhouette colours (z, 1, z^2) from the view-space depth itself (extra_colors
+                                * must be NULL) and chains dL/dz into dL_dmeans3D / dL_dviewmatrix in the backward —
+                                * no per-Gaussian host-side op at all (R/slam/renderer.py:26-43) */
     /* Extension: [P,3] extra per-Gaussian colours blended in the SAME pass into a second
      * [3,H,W] image (the SLAM renderer's depth / silhouette colours [z, 1, z^2], for which the reference
      * runs the whole rasterizer a second time, R/slam/renderer.py:207-214).  NULL = absent. */
@@ -112,7 +115,8 @@ typedef struct gsr_grads {
      * the keyframe-sharded map step) and skip one read-add-write pass per parameter per frame. */
     int32_t accumulate;
     int32_t _pad;
-    float* dL_dextra;      /* [P,3] (acc) gradient w.r.t. extra_colors; required iff extra_colors is given */
+    float* dL_dextra;      /* [P,3] (acc) gradient w.r.t. the extra colours; required iff extra colours are used
+                            * (with extra_mode 1 it is scratch: the chain to the means is applied in the library) */
 } gsr_grads;
 
 int gsr_abi_version(void);
@@ -141,7 +145,7 @@ int gsr_forward_preprocess(gsr_stream_t stream, const gsr_gaussians* g, const gs
 int gsr_forward_render(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                        const int32_t* radii, int64_t R,
                        void* geom_ws, void* binning_ws, size_t binning_ws_bytes, void* img_ws,
-                       float* out_color, float* out_extra /* [3,H,W]; required iff g->extra_colors */);
+                       float* out_color, float* out_extra /* [3,H,W]; required iff extra colours are used */);
 
 /* Backward of the whole call. */
 int gsr_backward(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,

@@ -87,6 +87,7 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.rects = carve<ushort4>(p, n);
     w.depth_keys = carve<uint32_t>(p, n);
     w.counters = carve<uint32_t>(p, 64);
+    w.extra_gen = carve<float>(p, n * 3);
     w.sort.keys_a = carve<uint32_t>(p, n);
     w.sort.vals_a = carve<uint32_t>(p, n);
     w.sort.keys_b = carve<uint32_t>(p, n);
@@ -164,6 +165,8 @@ static int check_common(const gsr_gaussians* g, const gsr_camera* cam)
             return fail(GSR_ERR_INVALID, "sh_degree / sh_coeffs inconsistent");
         if (!cam->viewmatrix || !cam->projmatrix || !cam->campos || !cam->background)
             return fail(GSR_ERR_INVALID, "camera pointers required");
+        if (g->extra_mode != 0 && (g->extra_mode != 1 || g->extra_colors))
+            return fail(GSR_ERR_INVALID, "extra_mode must be 0, or 1 with extra_colors == NULL");
     }
     return GSR_OK;
 }
@@ -255,6 +258,7 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     a.focal_y = H / (2.0f * cam->tanfovy);
     a.focal_x = W / (2.0f * cam->tanfovx);
     a.radii = radii; a.rec = gw.rec; a.rects = gw.rects; a.depth_keys = gw.depth_keys; a.num_rendered = gw.counters;
+    a.extra_gen = g->extra_mode == 1 ? gw.extra_gen : nullptr;
     prof_mark(ST_BEGIN, stream);
     GSR_CUDA(cudaMemsetAsync(gw.counters, 0, sizeof(uint32_t), stream));
     launch_preprocess_fwd(a, stream);
@@ -292,7 +296,8 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     cudaStream_t stream = (cudaStream_t)stream_;
     const int P = g->P, W = cam->width, H = cam->height;
     if (!out_color) return fail(GSR_ERR_INVALID, "out_color required");
-    if (g->extra_colors && !out_extra) return fail(GSR_ERR_INVALID, "out_extra required with extra_colors");
+    if ((g->extra_colors || g->extra_mode == 1) && !out_extra)
+        return fail(GSR_ERR_INVALID, "out_extra required with extra colours");
     if (R < 0 || R > 0x7fffffffLL) return fail(GSR_ERR_INVALID, "num_rendered out of range");
     if (P == 0) {  // reference: zero image, nothing else (DGR/rasterize_points.cu:81)
         GSR_CUDA(cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * (size_t)W * H, stream));
@@ -313,7 +318,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 4);
     launch_render_fwd(W, H, gx, gy, iw.ranges, iw.order, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
-                      out_color, bw.contrib, g->extra_colors, out_extra, stream);
+                      out_color, bw.contrib, g->extra_mode == 1 ? gw.extra_gen : g->extra_colors, out_extra, stream);
     GSR_STAGE("render", cam->debug, stream);
     GSR_MARK(ST_RENDER, stream, 1);
     return GSR_OK;
@@ -330,8 +335,9 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     if (!gr || !dL_dpixels || !radii || !geom_ws || !img_ws) return fail(GSR_ERR_INVALID, "null argument");
     if (!gr->dL_dmeans2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolors || !gr->dL_dmeans3D)
         return fail(GSR_ERR_INVALID, "required gradient buffer missing");
-    if (g->extra_colors && (!dL_dpixels_extra || !gr->dL_dextra))
-        return fail(GSR_ERR_INVALID, "dL_dpixels_extra / dL_dextra required with extra_colors");
+    const float* extra = g->extra_mode == 1 ? geom_ws_carve((char*)geom_ws, P, W, H).extra_gen : g->extra_colors;
+    if (extra && (!dL_dpixels_extra || !gr->dL_dextra))
+        return fail(GSR_ERR_INVALID, "dL_dpixels_extra / dL_dextra required with extra colours");
     const int M = g->shs ? g->sh_coeffs : 0;
     if ((M > 0 && !gr->dL_dsh) || (g->scales && (!gr->dL_dscales || !gr->dL_drotations)))
         return fail(GSR_ERR_INVALID, "gradient buffer for a provided input missing");
@@ -345,7 +351,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
         BinWS bw = bin_ws_carve((char*)binning_ws, R);
         launch_render_bwd(W, H, gx, gy, iw.ranges, iw.order, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
                           bw.contrib, dL_dpixels, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolors,
-                          g->extra_colors, dL_dpixels_extra, gr->dL_dextra, stream);
+                          extra, dL_dpixels_extra, gr->dL_dextra, stream);
         GSR_STAGE("render_backward", cam->debug, stream);
         GSR_MARK(ST_RENDER_BWD, stream, 1);
     }
@@ -362,6 +368,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     a.dL_dscales = gr->dL_dscales; a.dL_drots = gr->dL_drotations;
     a.dL_dview = gr->dL_dviewmatrix; a.dL_dproj = gr->dL_dprojmatrix; a.dL_dcampos = gr->dL_dcampos;
     a.accumulate = gr->accumulate;
+    a.dL_dextra_gen = g->extra_mode == 1 ? gr->dL_dextra : nullptr;
     launch_preprocess_bwd(a, stream);
     GSR_STAGE("preprocess_backward", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS_BWD, stream, 1);

@@ -33,6 +33,7 @@ struct GeomWS {
     ushort4* rects;        // tile rectangle {x0, y0, x1, y1}; empty for culled Gaussians
     uint32_t* depth_keys;  // float bits of the view depth; 0xFFFFFFFF for culled Gaussians
     uint32_t* counters;    // [0] = R (number of tile instances)
+    float* extra_gen;      // [P,3] generated (z, 1, z^2) colours (extra_mode 1)
     SortWS sort;
     size_t total;
 };
@@ -66,6 +67,7 @@ struct PreArgs {
     ushort4* rects;
     uint32_t* depth_keys;
     uint32_t* num_rendered;   // device counter, zeroed by the caller
+    float* extra_gen;         // [P,3] generated depth/silhouette colours (z, 1, z^2), or nullptr
 };
 void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, const float* proj, uint8_t* present,
@@ -96,6 +98,7 @@ struct PreBwdArgs {
     float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots;
     float *dL_dview, *dL_dproj, *dL_dcampos;
     int accumulate;
+    const float* dL_dextra_gen;   // [P,3] gradient of the generated (z, 1, z^2) colours, or nullptr
 };
 void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
 

@@ -131,6 +131,12 @@ __global__ void __launch_bounds__(kPB, 5) k_preprocess_fwd(PreArgs a)
                                                  (unsigned short)o.y1)
                                   : make_ushort4(0, 0, 0, 0);
         a.depth_keys[idx] = radius > 0 ? __float_as_uint(o.depth) : 0xffffffffu;
+        if (a.extra_gen != nullptr) {   // SLAM depth / silhouette colours (z, 1, z^2); R/slam/renderer.py:26-43
+            const float z = radius > 0 ? o.depth : 0.f;
+            a.extra_gen[(size_t)idx * 3 + 0] = z;
+            a.extra_gen[(size_t)idx * 3 + 1] = radius > 0 ? 1.f : 0.f;
+            a.extra_gen[(size_t)idx * 3 + 2] = z * z;
+        }
     }
     {   // R = total number of tile instances: warp reduce, one shared atomic per warp, one global per CTA
         const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)tiles);

@@ -109,6 +109,14 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
         dmean.x += dproj.x;
         dmean.y += dproj.y;
         dmean.z += dproj.z;
+        float dz_extra = 0.f;
+        if (a.dL_dextra_gen != nullptr) {   // generated colours (z, 1, z^2): dL/dz = dE0 + 2 z dE2, z = row 2 of view * [p;1]
+            const float z = a.rec[(size_t)idx * 3].z;
+            dz_extra = a.dL_dextra_gen[(size_t)idx * 3] + 2.f * z * a.dL_dextra_gen[(size_t)idx * 3 + 2];
+            dmean.x += view[2] * dz_extra;
+            dmean.y += view[6] * dz_extra;
+            dmean.z += view[10] * dz_extra;
+        }
         if (CAM) {
             // t = V[p;1]: dV[r][c] += dt[r] p[c]; flat index c*4 + r
             const float pc[4] = {m.x, m.y, m.z, 1.f};
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(kPB) k_preprocess_bwd(PreBwdArgs a)
 #pragma unroll
             for (int c = 0; c < 4; c++)
 #pragma unroll
-                for (int r = 0; r < 3; r++) cam[c * 4 + r] += dtv[r] * pc[c];
+                for (int r = 0; r < 3; r++) cam[c * 4 + r] += (dtv[r] + (r == 2 ? dz_extra : 0.f)) * pc[c];
             // A = J V3: dV3[r][c] = sum_i J[i][r] dA[i][c]
             const V3 t = cov2d_project(m, a.focal_x, a.focal_y, a.tanfovx, a.tanfovy, cov6, view).t;
             const float j00 = a.focal_x / t.z, j02 = -(a.focal_x * t.x) / (t.z * t.z);

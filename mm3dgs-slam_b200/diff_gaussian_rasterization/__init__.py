@@ -31,7 +31,8 @@ from typing import NamedTuple
 import torch
 import torch.nn as nn
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "prepare_forward"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "prepare_forward",
+           "DEPTH_SILHOUETTE"]
 
 # ------------------------------------------------------------------------------------------------
 # Library loading
@@ -47,7 +48,7 @@ class _Gaussians(ctypes.Structure):
         ("P", ctypes.c_int32), ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32), ("_pad", ctypes.c_int32),
         ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p),
         ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
-        ("cov3D_precomp", ctypes.c_void_p), ("scale_modifier", ctypes.c_float), ("_pad2", ctypes.c_int32),
+        ("cov3D_precomp", ctypes.c_void_p), ("scale_modifier", ctypes.c_float), ("extra_mode", ctypes.c_int32),
         ("extra_colors", ctypes.c_void_p),
     ]
 
@@ -130,12 +131,18 @@ def _snapshot(args, path):
 # ------------------------------------------------------------------------------------------------
 # Native calls
 # ------------------------------------------------------------------------------------------------
+DEPTH_SILHOUETTE = "depth_silhouette"   # extra_colors=DEPTH_SILHOUETTE: (z, 1, z^2) generated inside the library
+
+
 def _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
              extra=None):
+    """extra: None, a [P,3] tensor, or DEPTH_SILHOUETTE."""
     P = means3D.shape[0]
     M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
+    gen = isinstance(extra, str)
     g = _Gaussians(P, int(rs.sh_degree), M, 0, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
-                   _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp), float(rs.scale_modifier), 0, _ptr(extra))
+                   _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp), float(rs.scale_modifier), 1 if gen else 0,
+                   None if gen else _ptr(extra))
     c = _Camera(int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy), _ptr(view), _ptr(proj),
                 _ptr(campos), _ptr(bg), int(bool(rs.prefiltered)), int(bool(rs.debug)))
     return g, c
@@ -175,7 +182,7 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
         t = [_prep(x if x is not None else e, dev) for x in (means3D, shs, colors_precomp, opacities, scales, rotations,
                                                              cov3D_precomp, rs.viewmatrix, rs.projmatrix, rs.campos,
                                                              rs.bg)]
-        extra = _prep(extra_colors, dev)
+        extra = extra_colors if isinstance(extra_colors, str) else _prep(extra_colors, dev)
         P = means3D.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
         pf = PreparedFrame()
@@ -188,7 +195,8 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
         u8 = dict(dtype=torch.uint8, device=dev)
         pf.geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
         pf.img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
-        pf.g, pf.c = _structs(*t[:7], rs, *t[7:11], extra if (extra is not None and extra.numel()) else None)
+        pf.g, pf.c = _structs(*t[:7], rs, *t[7:11],
+                              extra if (isinstance(extra, str) or (extra is not None and extra.numel())) else None)
         _check(_lib.gsr_forward_preprocess(pf.stream.cuda_stream, ctypes.byref(pf.g), ctypes.byref(pf.c),
                                            pf.radii.data_ptr(), pf.geom.data_ptr(), pf.geom.numel(), pf.img.data_ptr(),
                                            pf.img.numel(), None))
@@ -212,7 +220,7 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
     u8 = dict(dtype=torch.uint8, device=dev)
     color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    has_extra = extra is not None and extra.numel() != 0
+    has_extra = isinstance(extra, str) or (extra is not None and extra.numel() != 0)
     extra_img = torch.empty((3, H, W), dtype=torch.float32, device=dev) if has_extra else None
     if P == 0:
         color.zero_()
@@ -275,7 +283,7 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
         g_scales = torch.empty((P, 3), **f32) if has_sr else None
         g_rots = torch.empty((P, 4), **f32) if has_sr else None
     g_cam = torch.zeros(35, **f32) if want_cam else None
-    has_extra = extra is not None and extra.numel() != 0
+    has_extra = isinstance(extra, str) or (extra is not None and extra.numel() != 0)
     g_extra = torch.zeros((P, 3), **f32) if has_extra else None
     if P == 0:
         return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra
@@ -335,10 +343,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         dev = means3D.device
         with torch.cuda.device(dev):
             t = [_prep(x, dev) for x in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                         viewmatrix, projmatrix, campos, rs.bg, extra_colors)]
-            means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, extra_ = t
-            if extra_ is not None and (extra_.dim() != 2 or extra_.shape != (means3D.shape[0], 3)):
-                raise RuntimeError("extra_colors must have dimensions (num_points, 3)")
+                                         viewmatrix, projmatrix, campos, rs.bg)]
+            means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_ = t
+            if isinstance(extra_colors, str):
+                if extra_colors != DEPTH_SILHOUETTE:
+                    raise ValueError("extra_colors must be a [P,3] tensor or diff_gaussian_rasterization.DEPTH_SILHOUETTE")
+                extra_ = extra_colors
+            else:
+                extra_ = _prep(extra_colors, dev)
+                if extra_ is not None and (extra_.dim() != 2 or extra_.shape != (means3D.shape[0], 3)):
+                    raise RuntimeError("extra_colors must have dimensions (num_points, 3)")
             args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_, prepared)
             if rs.debug:
                 try:
@@ -354,8 +368,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.has_extra = extra_img is not None
+        ctx.extra_gen = isinstance(extra_, str)
         ctx.save_for_backward(means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, radii,
-                              geom, binning, img, extra_ if ctx.has_extra else torch.empty(0))
+                              geom, binning, img,
+                              extra_ if (ctx.has_extra and not ctx.extra_gen) else torch.empty(0))
         ctx.mark_non_differentiable(radii)
         if ctx.has_extra:
             return color, radii, extra_img
@@ -377,7 +393,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_extra = _prep(grad_out_extra, dev) if grad_out_extra is not None else torch.zeros_like(grad)
             args = (grad, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj,
                     campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam, ctx.grad_targets,
-                    extra if ctx.has_extra else None, grad_extra)
+                    (DEPTH_SILHOUETTE if ctx.extra_gen else extra) if ctx.has_extra else None, grad_extra)
             if rs.debug:
                 try:
                     res = _backward_native(*args)
@@ -388,6 +404,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             else:
                 res = _backward_native(*args)
         g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra = res
+        if ctx.extra_gen:
+            g_extra = None          # the chain through z was applied inside the library
         has_colors = colors_precomp is not None and colors_precomp.numel() != 0
         g_view = g_proj = g_campos = None
         if g_cam is not None:
@@ -444,7 +462,8 @@ class GaussianRasterizer(nn.Module):
                 cov3D_precomp=None, grad_targets=None, extra_colors=None, prepared=None):
         """Reference signature and return value (color[3,H,W], radii[P]).  Extensions (keyword-only in spirit):
         `extra_colors` [P,3] -> returns (color, extra_image[3,H,W], radii): the extra colours are blended in the
-        same pass (the SLAM renderer's second, depth/silhouette call fused into the first);
+        same pass (the SLAM renderer's second, depth/silhouette call fused into the first); pass
+        extra_colors=DEPTH_SILHOUETTE to have the library generate (z, 1, z^2) from the view-space depth itself;
         `grad_targets`: see rasterize_gaussians; `prepared`: handle from prepare_forward()."""
         rs = self.raster_settings
         if (shs is None) == (colors_precomp is None):
