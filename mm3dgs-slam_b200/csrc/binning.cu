@@ -19,9 +19,12 @@
 //   count   : CTA-local histogram of a contiguous chunk (shared-memory atomics), one row of H[c][bin]
 //   scan    : per bin, exclusive prefix over the chunks (+ per-bin totals)
 //   scatter : exclusive scan over the bins (in shared memory), then each warp ranks its contiguous
-//             sub-chunk with __match_any_sync, in order, against its private counters.
-// HBM traffic: 3 x 16 B per Gaussian for the depth sort + 4 B per instance written once, instead of
-// the reference's ~150 B per instance (6 onesweep passes over 12-byte pairs).
+//             sub-chunk, in order, against its private counters (same-bin lanes of a 32-element step are
+//             matched with MATCH.ANY for digits / one ballot per bit for tile ids).
+// The tile partition additionally materialises the instance stream once ({tile, id} records, written
+// by warps that each own an equal share of their CTA's instances) so that the scatter pass is two
+// coalesced sweeps.  HBM traffic: 3 x 16 B per Gaussian for the depth sort + ~20 B per instance,
+// instead of the reference's ~150 B per instance (6 onesweep passes over 12-byte pairs).
 #include "gsr_internal.cuh"
 
 namespace gsr {
