@@ -52,6 +52,37 @@ class GradBucket:
         return self.flat.numel() * 4
 
 
+class DensificationStats:
+    """The per-Gaussian statistics the reference mapper accumulates next to the gradients, made
+    consistent across ranks:
+
+      max_radii2D[vis]        = max(max_radii2D[vis], radii[vis])          R/slam/mapper.py:892-895
+      xyz_gradient_accum[vis] += || viewspace_points.grad[vis, :2] ||      R/slam/gaussian_model.py:594-598
+      denom[vis]              += 1
+
+    The accumulated quantity is the SUM over keyframes of per-keyframe norms (not the norm of the summed
+    gradient), so every rank accumulates its own keyframes locally (`add`) and `reduce` then needs one
+    all-reduce(SUM) over the packed [2,P] (accum, denom) and one all-reduce(MAX) over [P] (radii)."""
+
+    def __init__(self, num_gaussians: int, device, group: Optional[dist.ProcessGroup] = None):
+        self.sum = torch.zeros(2, num_gaussians, dtype=torch.float32, device=device)   # [accum, denom]
+        self.max_radii = torch.zeros(num_gaussians, dtype=torch.float32, device=device)
+        self.group = group
+
+    def add(self, radii: torch.Tensor, viewspace_grad: torch.Tensor):
+        vis = radii > 0
+        self.sum[0] += torch.where(vis, viewspace_grad[:, :2].norm(dim=-1), torch.zeros((), device=radii.device))
+        self.sum[1] += vis.to(torch.float32)
+        self.max_radii = torch.maximum(self.max_radii, torch.where(vis, radii.to(torch.float32), self.max_radii))
+
+    def reduce(self):
+        """Returns (xyz_gradient_accum [P,1], denom [P,1], max_radii2D [P]) identical on every rank."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.sum, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.group)
+        return self.sum[0].unsqueeze(1), self.sum[1].unsqueeze(1), self.max_radii
+
+
 def shard_keyframes(num_keyframes: int, rank: int, world: int) -> List[int]:
     """Indices of the keyframes rank `rank` owns: r, r+G, r+2G, ..."""
     return list(range(rank, num_keyframes, world))

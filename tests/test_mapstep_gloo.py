@@ -95,3 +95,35 @@ def test_two_phase_schedule_matches_per_frame():
     out = b.step(cams)
     assert len(out) == len(cams)
     assert torch.allclose(a.bucket.flat, b.bucket.flat, rtol=1e-6, atol=1e-7 * float(a.bucket.flat.abs().max()))
+
+
+def _stats_worker(rank, world, port, out):
+    from gsr_mapstep import DensificationStats
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    st = DensificationStats(50, "cpu")
+    for kf in shard_keyframes(4, rank, world):
+        g = torch.Generator().manual_seed(100 + kf)
+        st.add(torch.randint(0, 5, (50,), generator=g), torch.randn(50, 3, generator=g))
+    res = st.reduce()
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_densification_stats_reduction(tmp_path):
+    from gsr_mapstep import DensificationStats
+    st = DensificationStats(50, "cpu")
+    for kf in range(4):
+        g = torch.Generator().manual_seed(100 + kf)
+        st.add(torch.randint(0, 5, (50,), generator=g), torch.randn(50, 3, generator=g))
+    want = st.reduce()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "stats.pt")
+    mp.spawn(_stats_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    for a, b in zip(got, want):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    assert float(want[1].max()) <= 4 and float(want[2].max()) <= 4
