@@ -284,6 +284,7 @@ def main():
         # consecutive keyframes alternate between two CUDA streams (binning of one overlaps blending of another)
         stepper = ShardedMapStep(params, forward_fn=forward_fn, streams=int(os.environ.get("GSR_BENCH_STREAMS", "4")),
                                  direct_targets=not os.environ.get("GSR_BENCH_NO_TARGETS"),
+                                 overwrite_first=not os.environ.get("GSR_BENCH_NO_OVERWRITE"),
                                  prepare_fn=None if os.environ.get("GSR_BENCH_NO_PREPARE") else prepare_fn)
         step = lambda: stepper.step(kfs)  # noqa: E731
         launch_count = dgr._lib.gsr_launch_count
@@ -367,7 +368,7 @@ def main():
     }
     if args.impl == "reference":
         line["impl"] = "reference"
-        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
+        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 1, "kind": "reference",
                                 "sample": "the reference's only implementation is CUDA: compiled unmodified from "
                                           "/root/reference for sm_100a (oracle/_ref) and run on this GPU, full workload"}
         line["e2e"] = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

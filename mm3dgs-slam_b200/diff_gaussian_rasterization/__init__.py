@@ -295,7 +295,7 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
                 g_cam.data_ptr() if want_cam else None,
                 g_cam.data_ptr() + 64 if want_cam else None,
                 g_cam.data_ptr() + 128 if want_cam else None,
-                1 if targets else 0, 0, _ptr(g_extra))
+                1 if (targets and not targets.get("_overwrite")) else 0, 0, _ptr(g_extra))
     _check(_lib.gsr_backward(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, _ptr(geom), _ptr(binning),
                              _ptr(img), grad_color.data_ptr(), _ptr(grad_extra_img) if has_extra else None,
                              ctypes.byref(gr)))
@@ -310,7 +310,9 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     """`grad_targets` (extension, optional): dict with fp32 contiguous accumulators for means3D, shs,
     opacities, scales, rotations.  The backward kernels then ADD this call's gradients straight into them
     (e.g. views of the map step's flat bucket) and autograd receives no gradient for those inputs — for
-    the case where the rasterizer inputs ARE the optimised tensors."""
+    the case where the rasterizer inputs ARE the optimised tensors.  With grad_targets["_overwrite"] = True
+    the kernels OVERWRITE means3D / shs / scales / rotations instead (first frame into a fresh accumulator:
+    no zero fill, no read-modify-write); the opacity accumulator must still be zero on entry."""
     rs = raster_settings
     out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos, grad_targets,

@@ -103,12 +103,17 @@ class ShardedMapStep:
 
     def __init__(self, params: Dict[str, torch.Tensor], frame_fn: Optional[Callable] = None,
                  group: Optional[dist.ProcessGroup] = None, forward_fn: Optional[Callable] = None,
-                 streams: int = 1, direct_targets: bool = False, prepare_fn: Optional[Callable] = None):
+                 streams: int = 1, direct_targets: bool = False, prepare_fn: Optional[Callable] = None,
+                 overwrite_first: bool = False):
         """streams > 1 (forward_fn mode, CUDA only): consecutive keyframes alternate between `streams` CUDA
         streams, so the latency-bound binning kernels of one frame overlap the blend kernels of another.
         direct_targets: forward_fn receives a third argument, a dict of gradient accumulators (views of a flat
         bucket, one bucket per stream) for kernels that add their gradients in place; the per-stream buckets
-        are summed into the main one before the all-reduce."""
+        are summed into the main one before the all-reduce.
+        overwrite_first (needs direct_targets, and a forward_fn that hands `targets` to the rasterizer's
+        grad_targets unchanged): the first frame written into each bucket in a step carries
+        targets["_overwrite"] = True, so the bucket needs no zero fill (only its opacity slice, which the blend
+        backward adds into) and that frame's gradients are stored instead of read-modify-written."""
         if (frame_fn is None) == (forward_fn is None):
             raise ValueError("give exactly one of frame_fn / forward_fn")
         self.params = params
@@ -121,6 +126,7 @@ class ShardedMapStep:
         self.prepare_fn = prepare_fn
         self.group = group
         self.direct_targets = direct_targets
+        self.overwrite_first = bool(overwrite_first and direct_targets)
         first = next(iter(params.values()))
         self.nstreams = max(1, int(streams)) if (forward_fn is not None and first.is_cuda) else 1
         self.streams = [torch.cuda.Stream(first.device) for _ in range(self.nstreams)] if self.nstreams > 1 else []
@@ -137,13 +143,16 @@ class ShardedMapStep:
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
 
-    def _targets(self, i):
+    def _targets(self, i, first=False):
+        """Accumulators of stream i.  `first`: this is the first frame written into them in this step, so the
+        kernels may overwrite (only the opacity slice, which the blend backward adds into, was zeroed)."""
         if not self.direct_targets:
             return None
-        return self.bucket.views if i == 0 else self.aux_views[i - 1]
+        views = self.bucket.views if i == 0 else self.aux_views[i - 1]
+        return dict(views, _overwrite=True) if (first and self.overwrite_first) else views
 
-    def _call_forward(self, kf, i, handle):
-        args = (self.params, kf) + ((self._targets(i),) if self.direct_targets else ())
+    def _call_forward(self, kf, i, handle, first=False):
+        args = (self.params, kf) + ((self._targets(i, first),) if self.direct_targets else ())
         if self.prepare_fn is not None:
             args = args + (handle,)
         return self.forward_fn(*args)
@@ -152,10 +161,15 @@ class ShardedMapStep:
         n = self.nstreams
         if n == 1:
             handles = [self.prepare_fn(self.params, kf) for kf in mine] if self.prepare_fn else [None] * len(mine)
-            return [self._call_forward(kf, 0, h) for kf, h in zip(mine, handles)]
+            return [self._call_forward(kf, 0, h, first=(j == 0)) for j, (kf, h) in enumerate(zip(mine, handles))]
         main = torch.cuda.current_stream()
-        for flat in self.aux_flat[: max(0, min(n, len(mine)) - 1)]:
-            flat.zero_()
+        used = max(0, min(n, len(mine)) - 1)
+        if self.overwrite_first:
+            for views in self.aux_views[:used]:
+                views["opacities"].zero_()      # the rest of a used per-stream bucket is overwritten by its first frame
+        else:
+            for flat in self.aux_flat[:used]:
+                flat.zero_()
         for st in self.streams:
             st.wait_stream(main)
         handles = [None] * len(mine)
@@ -166,7 +180,7 @@ class ShardedMapStep:
         outs = []
         for j, kf in enumerate(mine):
             with torch.cuda.stream(self.streams[j % n]):
-                outs.append(self._call_forward(kf, j % n, handles[j]))
+                outs.append(self._call_forward(kf, j % n, handles[j], first=(j < n)))
         return outs
 
     def my_keyframes(self, keyframes: Sequence):
@@ -187,13 +201,21 @@ class ShardedMapStep:
             self.params = saved
 
     def _step(self, keyframes: Sequence):
-        self.bucket.zero_()
+        mine = self.my_keyframes(keyframes)
+        if self.overwrite_first and self.forward_fn is not None and mine:
+            self.bucket.views["opacities"].zero_()
+        else:
+            self.bucket.zero_()
         if not self.direct_targets:
             self.bucket.attach()
-        mine = self.my_keyframes(keyframes)
         if self.forward_fn is not None:
             outs = self._forwards(mine)
-            if outs:
+            if outs and self.overwrite_first:
+                # the frame that overwrites a bucket must be back-propagated before the frames that add to it:
+                # one backward call per frame, in forward order (a joint call leaves the order to the engine)
+                for o, g in outs:
+                    torch.autograd.backward(o, g)
+            elif outs:
                 torch.autograd.backward([o for o, _ in outs], [g for _, g in outs])
             if self.nstreams > 1:
                 main = torch.cuda.current_stream()

@@ -278,26 +278,35 @@ def test_grad_targets_accumulate(dgr):
     cams = S.orbit_cameras(W, H, 2, (0.0, 0.0, 4.0), 0.4)
     names = ["means3D", "shs", "opacities", "scales", "rotations"]
 
-    def run(use_targets):
+    def run(use_targets, overwrite_first=False):
         p = {k: gs[k].clone().requires_grad_(True) for k in names}
         tg = {k: torch.zeros_like(v) for k, v in p.items()} if use_targets else None
+        if overwrite_first:     # stale contents everywhere except the opacity accumulator
+            for k in names:
+                if k != "opacities":
+                    tg[k].fill_(123.0)
         outs = []
-        for cam in cams:
+        for ci, cam in enumerate(cams):
             rs = settings_for(dgr, cam, bg, deg, dev)
             m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
             color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"],
                                                   shs=p["shs"], scales=p["scales"], rotations=p["rotations"],
-                                                  grad_targets=tg)
+                                                  grad_targets=dict(tg, _overwrite=True) if (overwrite_first and ci == 0) else tg)
             outs.append(color)
-        torch.autograd.backward(outs, [dL] * len(outs))
+        if overwrite_first:     # the overwriting frame must run first in the backward: do them one by one
+            for o in outs:
+                o.backward(dL)
+        else:
+            torch.autograd.backward(outs, [dL] * len(outs))
         if use_targets:
             assert all(v.grad is None for v in p.values())
             return tg
         return {k: v.grad for k, v in p.items()}
 
-    a, b = run(False), run(True)
+    a, b, c = run(False), run(True), run(True, overwrite_first=True)
     for k in names:
         assert rel_err(b[k], a[k]) < 1e-5, k
+        assert rel_err(c[k], a[k]) < 1e-5, k
 
 
 def _slam_case(dev, P=30000, W=320, H=240, deg=0, seed=51):
@@ -518,3 +527,33 @@ def test_native_pose_and_generated_depth_colours(dgr):
     # gradients differ (the native mode also differentiates cov2D w.r.t. the view rotation), their projections
     # onto valid poses must agree
     assert rel_err(qt2.grad, qt1.grad) < 5e-3, (qt2.grad, qt1.grad)
+
+
+def test_scaling_config_5m_1080p(dgr, ref):
+    """BASELINE config 5 geometry (5M Gaussians, 1920x1080): instance count, radii, the whole per-tile
+    depth-ordered list (compared on the device), contributor counts and the image against the reference."""
+    from tests.util import rel_err, scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 5_000_000, 1920, 1080
+    gs, cam, dL, bg = scene_on(dev, P, W, H, 0, 0)
+    rs = settings_for(dgr, cam, bg, 0, dev)
+    with torch.no_grad():
+        R, color, radii, geom, binning, img = dgr._forward_native(
+            gs["means3D"], gs["shs"], None, gs["opacities"], gs["scales"], gs["rotations"], None, rs,
+            rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+        f = ref.forward(gs["means3D"], gs["opacities"], rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg, W, H,
+                        cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], 0)
+    torch.cuda.synchronize()
+    assert R == f["num_rendered"] and R > 10_000_000
+    assert torch.equal(radii, f["radii"])
+    # both libraries keep the sorted Gaussian-id list first in their binning buffer
+    mine = binning[: 4 * R].view(torch.int32)
+    theirs = f["binning"][: 4 * R].view(torch.int32)
+    assert torch.equal(mine, theirs)
+    assert rel_err(color, f["color"]) < TOL
+    # backward runs and stays finite at this size
+    m = gs["means3D"].clone().requires_grad_(True)
+    c, _ = dgr.GaussianRasterizer(rs)(means3D=m, means2D=torch.zeros(P, 3, device=dev), opacities=gs["opacities"],
+                                      shs=gs["shs"], scales=gs["scales"], rotations=gs["rotations"])
+    (c * dL).sum().backward()
+    assert bool(torch.isfinite(m.grad).all()) and float(m.grad.abs().max()) > 0
