@@ -284,7 +284,9 @@ def main():
         # consecutive keyframes alternate between two CUDA streams (binning of one overlaps blending of another)
         stepper = ShardedMapStep(params, forward_fn=forward_fn, streams=int(os.environ.get("GSR_BENCH_STREAMS", "4")),
                                  direct_targets=not os.environ.get("GSR_BENCH_NO_TARGETS"),
-                                 overwrite_first=not os.environ.get("GSR_BENCH_NO_OVERWRITE"),
+                                 # (overwrite_first measured slower here: its per-frame backward calls make autograd
+                                 #  re-join the streams after every frame: 1705 vs 1861 frames/s)
+                                 overwrite_first=bool(os.environ.get("GSR_BENCH_OVERWRITE")),
                                  prepare_fn=None if os.environ.get("GSR_BENCH_NO_PREPARE") else prepare_fn)
         step = lambda: stepper.step(kfs)  # noqa: E731
         launch_count = dgr._lib.gsr_launch_count
