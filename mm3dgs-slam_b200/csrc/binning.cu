@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __rest
 }
 
 // Stable scatter of one digit pass.  vals_in == nullptr means "value = element index" (first pass).
-__global__ void __launch_bounds__(kSortThreads) k_digit_scatter(const uint32_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(kSortThreads, 2) k_digit_scatter(const uint32_t* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in, int n, int shift,
                                                                 uint32_t mask, const uint32_t* __restrict__ base,
                                                                 const uint32_t* __restrict__ totals,
@@ -176,18 +176,32 @@ __global__ void __launch_bounds__(kSortThreads) k_digit_scatter(const uint32_t* 
         const int i = wbase + j * 32 + lane;
         key[j] = (i < n) ? keys_in[i] : 0u;
     }
-    // counting sweep
+    // all matches first (independent of each other: eight MATCH.ANY in flight), then ONE dependent sweep over the
+    // per-warp counters that also leaves every element's rank inside the warp's sub-chunk in a register
+    unsigned peers[kSortItems];
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+        const int i = wbase + j * 32 + lane;
+        const uint32_t d = (i < n) ? ((key[j] >> shift) & mask) : 0xffffffffu;
+        peers[j] = __match_any_sync(kFullMask, d);   // digits of random keys: hardware MATCH measured faster than ballots
+    }
+    uint32_t ofs[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         const int i = wbase + j * 32 + lane;
         const bool valid = i < n;
-        const uint32_t d = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(kFullMask, d);   // digits of random keys: hardware MATCH measured faster
-        if (valid && (peers & lanemask_lt()) == 0) s_cnt[warp][d] += (uint16_t)__popc(peers);
+        const uint32_t d = (key[j] >> shift) & mask;
+        const int leader = __ffs(peers[j]) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = s_cnt[warp][d];
+            s_cnt[warp][d] = (uint16_t)(old + __popc(peers[j]));
+        }
+        ofs[j] = __shfl_sync(kFullMask, old, leader) + __popc(peers[j] & lanemask_lt());
         __syncwarp();
     }
     __syncthreads();
-    // exclusive prefix over the warps, per bin
+    // exclusive prefix over the warps, per bin (the counters now hold each warp's total per bin)
     for (int b = tid; b < kBins; b += kSortThreads) {
         uint32_t run = 0;
 #pragma unroll
@@ -198,26 +212,16 @@ __global__ void __launch_bounds__(kSortThreads) k_digit_scatter(const uint32_t* 
         }
     }
     __syncthreads();
-    // ranking sweep
+    // scatter: position = bin start of this CTA + elements of earlier warps + rank inside the warp
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         const int i = wbase + j * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t d = valid ? ((key[j] >> shift) & mask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(kFullMask, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = s_cnt[warp][d];
-            s_cnt[warp][d] = (uint16_t)(old + __popc(peers));
-        }
-        old = __shfl_sync(kFullMask, old, leader);
-        if (valid) {
-            const uint32_t pos = s_start[d] + old + __popc(peers & lanemask_lt());
+        if (i < n) {
+            const uint32_t d = (key[j] >> shift) & mask;
+            const uint32_t pos = s_start[d] + s_cnt[warp][d] + ofs[j];
             keys_out[pos] = key[j];
             vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
         }
-        __syncwarp();
     }
 }
 
