@@ -24,6 +24,7 @@ the 126 MB L2, so no explicit flush is needed between iterations (stated in conf
 import argparse
 import ctypes
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -227,6 +228,68 @@ def measure_m2(rasterize, settings_cls, params, dL, device, args, fused=None, it
         torch.cuda.synchronize()
         out[name + "_fps"] = iters / (e0.elapsed_time(e1) / 1e3)
     out["what"] = "full SLAM render (pose transform + RGB + depth/silhouette) fwd+bwd, 1 GPU, same scene"
+    return out
+
+
+def measure_iteration_ops(device, args, iters=20):
+    """the image loss (value + gradient) and the optimizer step of one mapping iteration,
+    library call vs the reference's torch composition (R/utils/loss_utils.py l1_loss + ssim + the masked depth L1 of
+    R/slam/mapper.py:839-860, restated inline; torch.optim.Adam as R/slam/gaussian_model.py:189) on the same GPU."""
+    import torch.nn.functional as F
+
+    import gsr_slam_ops as ops
+    W, H, P = args.W, args.H, args.P
+    d = {k: v.to(device) for k, v in S.make_loss_inputs(W, H, 3).items()}
+    cfg = ops.mapper_splatam()
+
+    def fused_loss():
+        ops.slam_loss_and_grads(cfg, d["image"], d["depth_image"], d["gt_color"], d["gt_depth"], d["gt_depth"])
+
+    g1 = torch.tensor([math.exp(-((x - 5) ** 2) / (2 * 1.5 ** 2)) for x in range(11)], device=device)
+    g1 = (g1 / g1.sum()).unsqueeze(1)
+    window = g1.mm(g1.t()).unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous()
+
+    def torch_loss():
+        img = d["image"].clone().requires_grad_(True)
+        dep = d["depth_image"].clone().requires_grad_(True)
+        gt = d["gt_color"]
+        mu1, mu2 = F.conv2d(img, window, padding=5, groups=3), F.conv2d(gt, window, padding=5, groups=3)
+        mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+        s1 = F.conv2d(img * img, window, padding=5, groups=3) - mu1_sq
+        s2 = F.conv2d(gt * gt, window, padding=5, groups=3) - mu2_sq
+        s12 = F.conv2d(img * gt, window, padding=5, groups=3) - mu12
+        ssim = (((2 * mu12 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1_sq + mu2_sq + 1e-4) * (s1 + s2 + 9e-4))).mean()
+        im = 0.8 * torch.abs(img - gt).mean() + 0.2 * (1.0 - ssim)
+        depth = dep[0]
+        unc = (dep[2] - depth ** 2).detach()
+        mask = ((d["gt_depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(unc))).detach()
+        (torch.abs(d["gt_depth"] - depth)[mask].mean() + 0.5 * im).backward()
+
+    n = 14 * P
+    flat = {"p": torch.randn(n, device=device)}
+    grads = torch.randn(n, device=device)
+    fa = ops.FlatAdam(flat, {"p": 1e-4})
+    tp = torch.randn(n, device=device, requires_grad=True)
+    tp.grad = grads.clone()
+    topt = torch.optim.Adam([tp], lr=1e-4, eps=1e-15)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    out = {"loss_us": timed(fused_loss), "loss_torch_us": timed(torch_loss),
+           "adam_us": timed(lambda: fa.step(grads)), "adam_torch_us": timed(topt.step)}
+    out["adam_gbs"] = 28.0 * n / (out["adam_us"] * 1e-6) / 1e9      # read p, g, m, v; write p, m, v
+    out["what"] = (f"mapping-iteration loss (L1 + SSIM + masked depth L1, value and gradient, {W}x{H}) and Adam step over the "
+                   f"{n}-float bucket: library call vs the torch composition the reference uses, microseconds per call")
     return out
 
 
@@ -524,6 +587,11 @@ def main():
                 dgr.GaussianRasterizationSettings, params, dL, device, args, fused=dgr.GaussianRasterizer)
         except Exception as ex:
             line["m2"] = {"error": repr(ex)}
+    if rank == 0 and world == 1:
+        try:
+            line["iteration_ops"] = measure_iteration_ops(device, args)
+        except Exception as ex:
+            line["iteration_ops"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args, gs_cpu, cams[0], dL_cpu)

@@ -49,6 +49,9 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess)
     return code;
 }
 
+int api_fail(int code, const char* what, cudaError_t e) { return fail(code, what, e); }
+void api_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 #define GSR_CUDA(expr)                                                     \
     do {                                                                   \
         cudaError_t _e = (expr);                                           \

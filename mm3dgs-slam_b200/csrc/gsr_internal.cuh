@@ -102,4 +102,8 @@ struct PreBwdArgs {
 };
 void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
 
+// ---- shared by the translation units that define extern "C" entry points (c_api.cu owns the state) ----
+int api_fail(int code, const char* what, cudaError_t e = cudaSuccess);   // records gsr_last_error(), returns code
+void api_count_launches(int n);                                          // feeds gsr_launch_count()
+
 }  // namespace gsr

@@ -1,0 +1,185 @@
+"""Host side of include/gsloss_b200.h: the image losses and the optimizer step that sit either side of the
+rasterizer in one MM3DGS-SLAM optimisation iteration.
+
+    slam_loss(cfg, image, depth_image, gt_color, depth_target, gt_depth) -> scalar (autograd)
+    slam_loss_and_grads(...) -> (losses[4], dL/dimage, dL/ddepth_image)    no autograd graph, no host sync
+    mapper_splatam / mapper_default / tracker_splatam / tracker_default    the reference's four compositions
+        (R/slam/mapper.py:839-885, R/slam/tracker.py:110-144) as configurations
+    FlatAdam       torch.optim.Adam(l, lr=0.0, eps=1e-15) of R/slam/gaussian_model.py:151-189 over one flat
+                   parameter / gradient / moment bucket, one launch per step
+
+Plumbing only (allocation + ctypes marshalling); all compute is in libgsrast_b200.so.  CUDA tensors only —
+there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from diff_gaussian_rasterization import _check, _lib
+
+COLOR_NONE, COLOR_L1_SSIM, COLOR_MASKED_L1_MEAN, COLOR_MASKED_L1_SUM = 0, 1, 2, 3
+DEPTH_NONE, DEPTH_L1_MEAN, DEPTH_L1_SUM, DEPTH_PEARSON, DEPTH_PEARSON_INV = 0, 1, 2, 3, 4
+MASK_GT_DEPTH_POS, MASK_NOT_NAN, MASK_SILHOUETTE = 1, 2, 4
+ADAM_MAX_SEGMENTS = 16
+
+
+class _LossConfig(ctypes.Structure):   # struct gsr_loss_config
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("color_mode", ctypes.c_int32),
+                ("depth_mode", ctypes.c_int32), ("color_mask", ctypes.c_int32), ("depth_mask", ctypes.c_int32),
+                ("lambda_dssim", ctypes.c_float), ("sil_threshold", ctypes.c_float), ("color_weight", ctypes.c_float),
+                ("depth_weight", ctypes.c_float), ("grad_scale", ctypes.c_float), ("_pad", ctypes.c_int32)]
+
+
+def _bind():
+    vp, i32, i64, sz, f32, f64 = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float,
+                                 ctypes.c_double)
+    _lib.gsr_slam_loss_ws_bytes.restype = sz
+    _lib.gsr_slam_loss_ws_bytes.argtypes = [i32, i32]
+    _lib.gsr_slam_loss.restype = ctypes.c_int
+    _lib.gsr_slam_loss.argtypes = [vp, ctypes.POINTER(_LossConfig), vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]
+    _lib.gsr_adam_step.restype = ctypes.c_int
+    _lib.gsr_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, ctypes.POINTER(i64), ctypes.POINTER(f64), f64, f64, f64,
+                                   i64, f32, i32]
+
+
+_bind()
+
+
+# ---- the reference's loss compositions -----------------------------------------------------------------------
+def mapper_splatam(lambda_dssim=0.2):
+    """losses["depth"] + 0.5 * losses["im"]   (R/slam/mapper.py:839-860)"""
+    return dict(color_mode=COLOR_L1_SSIM, lambda_dssim=lambda_dssim, depth_mode=DEPTH_L1_MEAN,
+                depth_mask=MASK_GT_DEPTH_POS | MASK_NOT_NAN, color_weight=0.5, depth_weight=1.0)
+
+
+def mapper_default(lambda_dssim=0.2, pearson_weight=0.05, use_gt_depth=False):
+    """(1-l) L1 + l (1 - SSIM) + w * pearson_loss(depth, est or gt, invert_estimate=False)   (R/slam/mapper.py:862-885)"""
+    return dict(color_mode=COLOR_L1_SSIM, lambda_dssim=lambda_dssim, depth_mode=DEPTH_PEARSON,
+                depth_mask=MASK_GT_DEPTH_POS if use_gt_depth else 0, color_weight=1.0, depth_weight=pearson_weight)
+
+
+def tracker_splatam():
+    """sum|gt_depth - depth|[mask] + 0.5 * sum|gt_color - image|[mask]   (R/slam/tracker.py:110-126)"""
+    m = MASK_GT_DEPTH_POS | MASK_NOT_NAN | MASK_SILHOUETTE
+    return dict(color_mode=COLOR_MASKED_L1_SUM, color_mask=m, depth_mode=DEPTH_L1_SUM, depth_mask=m,
+                sil_threshold=0.99, color_weight=0.5, depth_weight=1.0)
+
+
+def tracker_default(pearson_weight=0.05, use_gt_depth=False):
+    """mean|image - gt|[:, sil] + w * pearson_loss(depth, est or gt, mask, invert_estimate=True)   (R/slam/tracker.py:127-144)"""
+    return dict(color_mode=COLOR_MASKED_L1_MEAN, color_mask=MASK_SILHOUETTE, depth_mode=DEPTH_PEARSON_INV,
+                depth_mask=MASK_SILHOUETTE | (MASK_GT_DEPTH_POS if use_gt_depth else 0), sil_threshold=0.99,
+                color_weight=1.0, depth_weight=pearson_weight)
+
+
+def _f32c(t, name, shape=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"gsr_slam_ops: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"gsr_slam_ops: {name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t
+
+
+def slam_loss_and_grads(cfg: dict, image, depth_image, gt_color, depth_target=None, gt_depth=None,
+                        want_grad: bool = True, grad_scale: float = 1.0):
+    """One gsr_slam_loss call on torch's current stream.  Returns (losses, dL_dimage, dL_ddepth_image):
+    losses = device tensor [total, colour term, depth term, mean SSIM]; the gradient tensors are None for an
+    image the configuration does not use (or when want_grad is False).  Nothing here waits for the GPU."""
+    ref = image if image is not None else depth_image
+    if ref is None:
+        raise RuntimeError("gsr_slam_ops: image or depth_image required")
+    H, W = int(ref.shape[-2]), int(ref.shape[-1])
+    image = _f32c(image, "image", (3, H, W))
+    depth_image = _f32c(depth_image, "depth_image", (3, H, W))
+    gt_color = _f32c(gt_color, "gt_color", (3, H, W))
+    depth_target = _f32c(depth_target, "depth_target", (H, W))
+    gt_depth = _f32c(gt_depth, "gt_depth", (H, W))
+    dev = ref.device
+    c = _LossConfig(W, H, int(cfg.get("color_mode", 0)), int(cfg.get("depth_mode", 0)), int(cfg.get("color_mask", 0)),
+                    int(cfg.get("depth_mask", 0)), float(cfg.get("lambda_dssim", 0.2)), float(cfg.get("sil_threshold", 0.5)),
+                    float(cfg.get("color_weight", 1.0)), float(cfg.get("depth_weight", 1.0)), float(grad_scale), 0)
+    with torch.cuda.device(dev):
+        ws = torch.empty(_lib.gsr_slam_loss_ws_bytes(W, H), dtype=torch.uint8, device=dev)
+        losses = torch.empty(4, dtype=torch.float32, device=dev)
+        d_img = torch.empty_like(image) if (want_grad and c.color_mode != COLOR_NONE) else None
+        d_dep = torch.empty_like(depth_image) if (want_grad and c.depth_mode != DEPTH_NONE) else None
+        p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+        _check(_lib.gsr_slam_loss(torch.cuda.current_stream(dev).cuda_stream, ctypes.byref(c), p(image), p(depth_image),
+                                  p(gt_color), p(depth_target), p(gt_depth), ws.data_ptr(), ws.numel(), losses.data_ptr(),
+                                  p(d_img), p(d_dep)))
+    return losses, d_img, d_dep
+
+
+class _SlamLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, depth_image, gt_color, depth_target, gt_depth, cfg):
+        need = (image is not None and image.requires_grad) or (depth_image is not None and depth_image.requires_grad)
+        losses, d_img, d_dep = slam_loss_and_grads(cfg, image, depth_image, gt_color, depth_target, gt_depth, want_grad=need)
+        ctx.grads = (d_img, d_dep)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        d_img, d_dep = ctx.grads
+        return (None if d_img is None else d_img * g_total, None if d_dep is None else d_dep * g_total,
+                None, None, None, None)
+
+
+def slam_loss(cfg: dict, image, depth_image, gt_color, depth_target=None, gt_depth=None, return_terms: bool = False):
+    """Differentiable scalar loss (w.r.t. image and depth_image).  return_terms: also the [total, colour, depth, ssim]
+    device tensor."""
+    total, losses = _SlamLoss.apply(image, depth_image, gt_color, depth_target, gt_depth, cfg)
+    return (total, losses) if return_terms else total
+
+
+# ---- Adam over a flat bucket ---------------------------------------------------------------------------------
+class FlatAdam:
+    """`params`: dict name -> tensor; the tensors are re-homed as views of ONE flat fp32 buffer (`self.flat`, same
+    order), so that parameters, gradients (a GradBucket-style flat tensor with the same layout) and both Adam moments
+    are four parallel arrays and a step is one kernel launch.  `lrs`: dict name -> learning rate (host floats; update
+    `self.lrs[name]` between steps for a schedule, R/slam/gaussian_model.py:196-202)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15):
+        if len(params) > ADAM_MAX_SEGMENTS:
+            raise ValueError(f"at most {ADAM_MAX_SEGMENTS} parameter groups")
+        first = next(iter(params.values()))
+        if not first.is_cuda:
+            raise RuntimeError("FlatAdam: CUDA tensors only (there is no CPU path)")
+        self.names = list(params.keys())
+        n = sum(p.numel() for p in params.values())
+        self.flat = torch.empty(n, dtype=torch.float32, device=first.device)
+        self.views: Dict[str, torch.Tensor] = {}
+        ends, off = [], 0
+        for k, p in params.items():
+            v = self.flat[off: off + p.numel()].view(p.shape)
+            v.copy_(p.detach())
+            self.views[k] = v
+            off += p.numel()
+            ends.append(off)
+        self.seg_end = (ctypes.c_int64 * len(ends))(*ends)
+        self.lrs = dict(lrs)
+        self.beta1, self.beta2 = float(betas[0]), float(betas[1])
+        self.eps = float(eps)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.steps = 0
+
+    def step(self, flat_grads: torch.Tensor, grad_scale: float = 1.0, zero_grads: bool = False):
+        if flat_grads.numel() != self.flat.numel() or flat_grads.dtype != torch.float32 or not flat_grads.is_contiguous() \
+                or flat_grads.device != self.flat.device:
+            raise RuntimeError("FlatAdam.step: gradient bucket must be a contiguous fp32 CUDA tensor of the parameter size")
+        self.steps += 1
+        lr = (ctypes.c_double * len(self.names))(*[float(self.lrs[k]) for k in self.names])
+        with torch.cuda.device(self.flat.device):
+            _check(_lib.gsr_adam_step(torch.cuda.current_stream(self.flat.device).cuda_stream, self.flat.data_ptr(),
+                                      flat_grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                      self.flat.numel(), len(self.names), self.seg_end, lr, self.beta1, self.beta2, self.eps,
+                                      self.steps, float(grad_scale), int(bool(zero_grads))))

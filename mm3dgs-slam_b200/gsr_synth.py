@@ -118,3 +118,27 @@ def make_scene(P, W, H, seed=0, sh_degree=0):
     dL = torch.randn(3, H, W, generator=g)
     bg = torch.zeros(3)
     return gs, cam, dL, bg
+
+
+def make_loss_inputs(W, H, seed=0, nan_frac=0.002):
+    """Seeded synthetic inputs of the image losses (CPU tensors): a rendered colour image and a ground truth that is
+    a blurred, noisy copy of it (so SSIM is away from both 0 and 1), a rendered (depth, silhouette, depth^2) image with
+    a band of low silhouette, a few NaN depths, and a ground-truth / estimated depth pair with invalid (zero) pixels."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    base = torch.stack([0.5 + 0.4 * torch.sin(7 * xx + 3 * yy), 0.5 + 0.4 * torch.cos(5 * yy - 2 * xx), 0.3 + 0.5 * xx * yy])
+    image = (base + 0.08 * torch.randn(3, H, W, generator=g)).clamp(0, 1)
+    gt = torch.nn.functional.avg_pool2d(image.unsqueeze(0), 3, 1, 1).squeeze(0) + 0.05 * torch.randn(3, H, W, generator=g)
+    gt = gt.clamp(0, 1)
+    depth = 2.0 + 1.5 * torch.sin(4 * xx) * torch.cos(3 * yy) + 0.05 * torch.randn(H, W, generator=g)
+    sil = (0.6 + 0.6 * torch.rand(H, W, generator=g)).clamp(max=1.0)
+    sil[:, : max(1, W // 10)] = 0.3 * torch.rand(H, max(1, W // 10), generator=g)      # unobserved band
+    depth_sq = depth ** 2 + 0.02 * torch.rand(H, W, generator=g)
+    nan = torch.rand(H, W, generator=g) < nan_frac
+    depth = torch.where(nan, torch.full_like(depth, float("nan")), depth)
+    gt_depth = (depth.nan_to_num(2.0) + 0.1 * torch.randn(H, W, generator=g)).clamp(min=0.2)
+    gt_depth = torch.where(torch.rand(H, W, generator=g) < 0.1, torch.zeros_like(gt_depth), gt_depth)   # invalid pixels
+    est_depth = 0.5 * gt_depth + 0.3 + 0.05 * torch.randn(H, W, generator=g)           # monocular: affine, noisy
+    return dict(image=image.float().contiguous(), gt_color=gt.float().contiguous(),
+                depth_image=torch.stack([depth, sil, depth_sq]).float().contiguous(),
+                gt_depth=gt_depth.float().contiguous(), est_depth=est_depth.float().contiguous())

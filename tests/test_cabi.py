@@ -9,17 +9,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "gsrast_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(gsr_[a-z_0-9]+)\s*\(", src)))
+    syms = set()
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if h.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", h)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            syms |= set(re.findall(r"\b(gsr_[a-z_0-9]+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_header_symbols_exported(built_lib):
     lib = ctypes.CDLL(built_lib)
     syms = _declared_symbols()
-    assert len(syms) >= 12
+    assert len(syms) >= 15 and "gsr_slam_loss" in syms and "gsr_adam_step" in syms
     for s in syms:
-        assert hasattr(lib, s), f"{s} declared in include/gsrast_b200.h but not exported"
+        assert hasattr(lib, s), f"{s} declared in include/*.h but not exported"
     lib.gsr_abi_version.restype = ctypes.c_int
     assert lib.gsr_abi_version() == 3
 
@@ -32,6 +36,32 @@ def test_struct_mirrors_match_c_layout(built_lib):
     assert ctypes.sizeof(dgr._Camera) == 16 + 4 * 8 + 8
     assert dgr._Camera.viewmatrix.offset == 16 and dgr._Camera.prefiltered.offset == 48
     assert ctypes.sizeof(dgr._Grads) == 12 * 8 + 8 + 8 and dgr._Grads.accumulate.offset == 96 and dgr._Grads.dL_dextra.offset == 104
+    import gsr_slam_ops as ops
+    assert ctypes.sizeof(ops._LossConfig) == 48 and ops._LossConfig.lambda_dssim.offset == 24   # 6 x int32, 5 x float, pad
+
+
+def test_slam_ops_reject_cpu_tensors_and_bad_arguments(built_lib):
+    """No CPU path for the loss / optimizer either; argument checks answer before any launch."""
+    import pytest
+    import torch
+
+    import gsr_slam_ops as ops
+    img = torch.rand(3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.slam_loss(ops.mapper_splatam(), img, img, img, img[0], img[0])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.FlatAdam({"a": torch.zeros(4)}, {"a": 1e-3})
+    lib = ctypes.CDLL(built_lib)
+    lib.gsr_slam_loss_ws_bytes.restype = ctypes.c_size_t
+    assert lib.gsr_slam_loss_ws_bytes(640, 480) >= 9 * 640 * 480 * 4
+    assert lib.gsr_slam_loss_ws_bytes(0, 480) == 0
+    lib.gsr_last_error.restype = ctypes.c_char_p
+    assert lib.gsr_slam_loss(None, None, None, None, None, None, None, None, 0, None, None, None) == -1
+    assert b"null" in lib.gsr_last_error()
+    lib.gsr_adam_step.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                          ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                                          ctypes.c_float, ctypes.c_int32]
+    assert lib.gsr_adam_step(None, None, None, None, None, 8, 1, None, None, 0.9, 0.999, 1e-15, 0, 1.0, 0) == -1   # step < 1
 
 
 def test_python_surface_matches_reference(built_lib):
