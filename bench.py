@@ -231,6 +231,100 @@ def measure_m2(rasterize, settings_cls, params, dL, device, args, fused=None, it
     return out
 
 
+def ssim_window(device):
+    g1 = torch.tensor([math.exp(-((x - 5) ** 2) / (2 * 1.5 ** 2)) for x in range(11)], device=device)
+    g1 = (g1 / g1.sum()).unsqueeze(1)
+    return g1.mm(g1.t()).unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous()
+
+
+def torch_mapping_loss(img, dep, gt, gt_depth, window):
+    """BASELINE leg only: the torch composition the reference's mapper runs per iteration, restated inline —
+    l1_loss + ssim (R/utils/loss_utils.py:64-68,114-154) and the masked depth L1 of R/slam/mapper.py:839-860."""
+    import torch.nn.functional as F
+    mu1, mu2 = F.conv2d(img, window, padding=5, groups=3), F.conv2d(gt, window, padding=5, groups=3)
+    mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(img * img, window, padding=5, groups=3) - mu1_sq
+    s2 = F.conv2d(gt * gt, window, padding=5, groups=3) - mu2_sq
+    s12 = F.conv2d(img * gt, window, padding=5, groups=3) - mu12
+    ssim = (((2 * mu12 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1_sq + mu2_sq + 1e-4) * (s1 + s2 + 9e-4))).mean()
+    im = 0.8 * torch.abs(img - gt).mean() + 0.2 * (1.0 - ssim)
+    depth = dep[0]
+    unc = (dep[2] - depth ** 2).detach()
+    mask = ((gt_depth > 0) & (~torch.isnan(depth)) & (~torch.isnan(unc))).detach()
+    return torch.abs(gt_depth - depth)[mask].mean() + 0.5 * im
+
+
+LRS = {"means3D": 1.6e-4, "shs": 2.5e-3, "opacities": 5e-2, "scales": 1e-3, "rotations": 1e-3}   # R/configs/TUM.yml mapping
+
+
+def measure_m3(impl, rasterize, settings_cls, params, device, args, iters=10):
+    """M3-style figure, one mapping iteration as the reference runs it (R/slam/mapper.py:797-939:
+    one keyframe per Adam step): full render (RGB + depth/silhouette) -> L1 + SSIM + masked depth L1 -> backward ->
+    Adam step -> zero_grad, iterations/s on one GPU.
+      impl "reference": the reference's call pattern — python pose transform, two rasterizer calls (tests/slam_glue.py),
+                        the torch loss composition, torch.optim.Adam(lr=0.0, eps=1e-15) over the parameter groups;
+      impl "b200":      one fused RGB+depth rasterizer call (library camera path, generated depth colours), gsr_slam_loss,
+                        backward straight into the flat gradient bucket, gsr_adam_step with in-pass zero_grad."""
+    from tests import slam_glue
+    P, W, H = args.P, args.W, args.H
+    bg = torch.zeros(3, device=device)
+    w2c = S.look_at_w2c((0.3, -0.1, 0.2), (0.0, 0.0, 4.0)).to(device)
+    g = torch.Generator().manual_seed(5)
+    gt_color = torch.rand(3, H, W, generator=g).to(device)
+    gt_depth = (torch.rand(H, W, generator=g) * 4 + 0.5).to(device)
+    names = [k for k in LRS if k in params]
+
+    if impl == "reference":
+        rs = slam_glue.settings(settings_cls, W, H, bg, args.sh_degree, device)
+        p = {k: params[k].detach().clone().requires_grad_(True) for k in names}
+        opt = torch.optim.Adam([{"params": [p[k]], "lr": LRS[k], "name": k} for k in names], lr=0.0, eps=1e-15)
+        window = ssim_window(device)
+
+        def iteration():
+            rgb, depth, _, _ = slam_glue.render_two_pass(rasterize, rs, p, w2c)
+            torch_mapping_loss(rgb, depth, gt_color, gt_depth, window).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+    else:
+        import diff_gaussian_rasterization as dgr_
+        import gsr_slam_ops as ops
+        from gsr_mapstep import GradBucket
+        opt = ops.FlatAdam({k: params[k].detach() for k in names}, LRS, eps=1e-15)
+        p = {k: v.requires_grad_(True) for k, v in opt.views.items()}
+        bucket = GradBucket(p)
+        view = w2c.t().contiguous()
+        proj = (view @ S.projection_matrix(*S.intrinsics(W, H), W, H).t().to(device)).contiguous()
+        cam = S.make_camera(W, H)
+        rs = settings_cls(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
+                          viewmatrix=view, projmatrix=proj, sh_degree=args.sh_degree,
+                          campos=torch.linalg.inv(view)[3, :3].contiguous(), prefiltered=False, debug=False)
+        cfg = ops.mapper_splatam()
+        m2 = torch.zeros(P, 3, device=device, requires_grad=True)
+
+        def iteration():
+            rgb, depth, _ = rasterize(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"], shs=p["shs"],
+                                          scales=p["scales"], rotations=p["rotations"], extra_colors=dgr_.DEPTH_SILHOUETTE,
+                                          grad_targets=bucket.views)
+            _, g_img, g_dep = ops.slam_loss_and_grads(cfg, rgb, depth, gt_color, gt_depth, gt_depth)
+            torch.autograd.backward([rgb, depth], [g_img, g_dep])
+            opt.step(bucket.flat, zero_grads=True)
+            m2.grad = None
+
+    for _ in range(3):
+        iteration()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        iteration()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"iterations_per_s": 1e3 / ms, "ms_per_iteration": ms,
+            "what": "one mapping iteration (render RGB+depth, L1+SSIM+depth loss, backward, Adam step, zero_grad), 1 GPU, "
+                    "1 keyframe per step as in the reference mapper"}
+
+
 def measure_iteration_ops(device, args, iters=20):
     """the image loss (value + gradient) and the optimizer step of one mapping iteration,
     library call vs the reference's torch composition (R/utils/loss_utils.py l1_loss + ssim + the masked depth L1 of
@@ -245,25 +339,12 @@ def measure_iteration_ops(device, args, iters=20):
     def fused_loss():
         ops.slam_loss_and_grads(cfg, d["image"], d["depth_image"], d["gt_color"], d["gt_depth"], d["gt_depth"])
 
-    g1 = torch.tensor([math.exp(-((x - 5) ** 2) / (2 * 1.5 ** 2)) for x in range(11)], device=device)
-    g1 = (g1 / g1.sum()).unsqueeze(1)
-    window = g1.mm(g1.t()).unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous()
+    window = ssim_window(device)
 
     def torch_loss():
         img = d["image"].clone().requires_grad_(True)
         dep = d["depth_image"].clone().requires_grad_(True)
-        gt = d["gt_color"]
-        mu1, mu2 = F.conv2d(img, window, padding=5, groups=3), F.conv2d(gt, window, padding=5, groups=3)
-        mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-        s1 = F.conv2d(img * img, window, padding=5, groups=3) - mu1_sq
-        s2 = F.conv2d(gt * gt, window, padding=5, groups=3) - mu2_sq
-        s12 = F.conv2d(img * gt, window, padding=5, groups=3) - mu12
-        ssim = (((2 * mu12 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1_sq + mu2_sq + 1e-4) * (s1 + s2 + 9e-4))).mean()
-        im = 0.8 * torch.abs(img - gt).mean() + 0.2 * (1.0 - ssim)
-        depth = dep[0]
-        unc = (dep[2] - depth ** 2).detach()
-        mask = ((d["gt_depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(unc))).detach()
-        (torch.abs(d["gt_depth"] - depth)[mask].mean() + 0.5 * im).backward()
+        torch_mapping_loss(img, dep, d["gt_color"], d["gt_depth"], window).backward()
 
     n = 14 * P
     flat = {"p": torch.randn(n, device=device)}
@@ -442,6 +523,11 @@ def main():
                                     dL, device, args)
         except Exception as ex:
             line["m2"] = {"error": repr(ex)}
+        try:
+            line["m3"] = measure_m3("reference", lambda m3, m2, op, rs_, **kw: ref_api.rasterize(m3, m2, op, rs_, **kw), RS,
+                                    params, device, args)
+        except Exception as ex:
+            line["m3"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -588,6 +674,10 @@ def main():
         except Exception as ex:
             line["m2"] = {"error": repr(ex)}
     if rank == 0 and world == 1:
+        try:
+            line["m3"] = measure_m3("b200", dgr.GaussianRasterizer, dgr.GaussianRasterizationSettings, params, device, args)
+        except Exception as ex:
+            line["m3"] = {"error": repr(ex)}
         try:
             line["iteration_ops"] = measure_iteration_ops(device, args)
         except Exception as ex:

@@ -49,7 +49,7 @@ def _run(cmd, verbose):
 
 
 def build(force=False, verbose=False, ptxas_info=False, defines=(), out=None):
-    """defines/out: build an experimental variant (e.g. defines=["GSR_TILE_MATCH_HW=1"], out=".../libvariant.so")."""
+    """defines/out: build an experimental variant (e.g. defines=["MY_SWITCH=1"], out=".../libvariant.so") for A/B runs."""
     global SO
     if out is None and not force and not needs_build():
         return SO

@@ -34,10 +34,7 @@ constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;       // 2048
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-#ifndef GSR_SORT_ITEMS
-#define GSR_SORT_ITEMS 8
-#endif
-constexpr int kSortItems = GSR_SORT_ITEMS;   // keys per thread
+constexpr int kSortItems = 8;                // keys per thread (4 measured slower)
 constexpr int kSortChunk = kSortThreads * kSortItems;   // 4096 keys per CTA
 
 int sort_chunks(int P) { return (P + kSortChunk - 1) / kSortChunk; }
@@ -413,17 +410,15 @@ __global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict_
 }
 
 // Exclusive scan of the per-tile totals -> ranges[t] = {start, end}.  Single CTA, any T.
-// Also emits `order`: the tile ids sorted by descending list length (log2 buckets) so that the blend
-// kernels start their heaviest tiles first and the light ones fill the tail of the launch.
+// (A heaviest-tiles-first launch order for the blend kernels was tried here and measured no gain on scenes whose
+// tiles carry similar loads; the blend kernels take tiles in index order.)
 __global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict__ totals, int T, uint2* __restrict__ ranges,
-                                                      uint32_t* __restrict__ starts, uint32_t* __restrict__ order)
+                                                      uint32_t* __restrict__ starts)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
-    __shared__ uint32_t s_bucket[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
-    if (tid < 33) s_bucket[tid] = 0;
     __syncthreads();
     for (int t0 = 0; t0 < T; t0 += 1024) {
         const int t = t0 + tid;
@@ -443,34 +438,18 @@ __global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict
         if (t < T) {
             starts[t] = start;
             ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
-            atomicAdd(&s_bucket[32 - __clz(v)], 1u);   // bucket 0: empty, bucket b: 2^(b-1) <= v < 2^b
         }
         __syncthreads();
         if (tid == 1023) s_carry = carry + wb + incl;
         __syncthreads();
     }
-    if (tid == 0) {   // descending buckets -> exclusive starts
-        uint32_t run = 0;
-        for (int b = 32; b >= 0; b--) {
-            const uint32_t c = s_bucket[b];
-            s_bucket[b] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-    for (int t = tid; t < T; t += 1024) order[atomicAdd(&s_bucket[32 - __clz(totals[t])], 1u)] = (uint32_t)t;
 }
 
-#ifndef GSR_TILE_MATCH_HW
-#define GSR_TILE_MATCH_HW 0
-#endif
+// Lanes holding the same tile id.  Ballot-per-bit: tile ids need few bits and neighbouring instances repeat
+// them, where the hardware MATCH (used for the random depth digits above) measured slower.
 __device__ __forceinline__ unsigned tile_peers(uint32_t tile, bool valid, int tbits)
 {
-#if GSR_TILE_MATCH_HW
-    return __match_any_sync(kFullMask, valid ? tile : 0xffffffffu);
-#else
     return match_any_bits(tile, valid, tbits);
-#endif
 }
 
 // Pass B.  Same CTA / warp <-> Gaussian-range mapping as pass A; no enumeration any more: each warp
@@ -573,16 +552,7 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
     warps = 32;
     while (warps > 1 && (size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024) warps >>= 1;
     if ((size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
-#ifdef GSR_PLAN_SINGLE_WAVE
-    // one resident wave: CTAs per SM limited by shared memory and by 2048 threads
-    const size_t smem1 = (size_t)T * (4 + 2 * (size_t)(warps > 0 ? warps : 1));
-    int per_sm = (int)((220 * 1024) / (smem1 ? smem1 : 1));
-    per_sm = per_sm < 1 ? 1 : per_sm;
-    if (per_sm * warps * 32 > 2048) per_sm = 2048 / (warps * 32 > 0 ? warps * 32 : 32);
-    const int max_ctas = 148 * (per_sm < 1 ? 1 : per_sm);
-#else
-    const int max_ctas = 4 * 148;
-#endif
+    const int max_ctas = 4 * 148;   // (sizing to exactly one resident wave measured slower)
     per_cta = 64 * (warps > 0 ? warps : 1);
     if (per_cta < 1024) per_cta = 1024;
     if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
@@ -598,7 +568,7 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
 }
 
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint32_t* order, uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s)
+                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;
     int ctas, per_cta, warps;
@@ -612,7 +582,7 @@ int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int
     cudaMemsetAsync(claim, 0, sizeof(uint32_t), s);
     k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, claim);
     k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals);
-    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts, order);
+    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts);
     k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list);
     return 0;
 }

@@ -117,7 +117,6 @@ ImgWS img_ws_carve(char* base, int W, int H)
     w.final_T = carve<float>(p, N);
     w.n_contrib = carve<uint32_t>(p, N);
     w.ranges = carve<uint2>(p, tiles);
-    w.order = carve<uint32_t>(p, tiles);
     w.total = (size_t)(p - base);
     return w;
 }
@@ -316,11 +315,11 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, iw.order, bw.stream, gw.counters + 1, bw.point_list, stream) != 0)
+    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters + 1, bw.point_list, stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 4);
-    launch_render_fwd(W, H, gx, gy, iw.ranges, iw.order, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
+    launch_render_fwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
                       out_color, bw.contrib, g->extra_mode == 1 ? gw.extra_gen : g->extra_colors, out_extra, stream);
     GSR_STAGE("render", cam->debug, stream);
     GSR_MARK(ST_RENDER, stream, 1);
@@ -352,7 +351,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     if (R > 0) {
         if (!binning_ws) return fail(GSR_ERR_INVALID, "binning workspace required");
         BinWS bw = bin_ws_carve((char*)binning_ws, R);
-        launch_render_bwd(W, H, gx, gy, iw.ranges, iw.order, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
+        launch_render_bwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
                           bw.contrib, dL_dpixels, gr->dL_dmeans2D, gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolors,
                           extra, dL_dpixels_extra, gr->dL_dextra, stream);
         GSR_STAGE("render_backward", cam->debug, stream);

@@ -41,7 +41,6 @@ struct ImgWS {
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
-    uint32_t* order;   // tile ids, heaviest first (launch order of the blend kernels)
     size_t total;
 };
 struct BinWS {
@@ -75,12 +74,12 @@ void launch_mark_visible(int P, const float* means, const float* view, const flo
 
 void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s);
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint32_t* order, uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s);
+                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s);
 
-void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
+void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
                        uint8_t* contrib, const float* extra, float* out_extra, cudaStream_t s);
-void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
+void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
                        const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
                        float* dL_dopacity, float* dL_dcolors /*[P,3]*/, const float* extra, const float* dL_dpix_extra,

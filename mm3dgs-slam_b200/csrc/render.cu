@@ -26,16 +26,8 @@
 
 namespace gsr {
 
-#ifndef GSR_FWD_MIN_CTAS
-#define GSR_FWD_MIN_CTAS 8
-#endif
-// Heaviest-tiles-first launch order (k_tile_starts) is available but off by default: on the benchmark
-// scenes, whose tiles carry similar loads, it measured no gain.
-#ifdef GSR_TILE_ORDER
-#define GSR_TILE_OF_BLOCK ((int)order[blockIdx.x])
-#else
-#define GSR_TILE_OF_BLOCK ((int)blockIdx.x)
-#endif
+constexpr int kFwdMinCtas = 8;   // resident CTAs per SM the forward blend is compiled for (6 with the extra channels)
+constexpr int kBwdMinCtas = 5;   // backward blend (4 with the extra channels); 6 measured slower (spills)
 constexpr int kBatch = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -103,8 +95,8 @@ __device__ __forceinline__ bool subtile_hit_ellipse(const TileGeom& g, float cx,
 // preprocess + one sort + one traversal instead of the reference's second full rasterizer call
 // (R/slam/renderer.py:196-214).
 template <bool EXTRA>
-__global__ void __launch_bounds__(256, EXTRA ? 6 : GSR_FWD_MIN_CTAS) k_render_fwd(
-    int W, int H, int gx, const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
+    int W, int H, int gx, const uint2* __restrict__ ranges,
     const uint32_t* __restrict__ point_list, const float4* __restrict__ rec, const float* __restrict__ bg,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
     uint8_t* __restrict__ contrib, const float* __restrict__ extra, float* __restrict__ out_extra)
@@ -115,7 +107,7 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : GSR_FWD_MIN_CTAS) k_render_fw
     __shared__ float s_ex[EXTRA ? kBatch * 3 : 1];
     __shared__ uint32_t s_mask[2][kBatch / 32][8];   // [buffer][32-entry group][warp]: entries this warp blended
 
-    const int tile = GSR_TILE_OF_BLOCK;
+    const int tile = ((int)blockIdx.x);
     const TileGeom g = tile_geom(tile, gx, W, H);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float pixx = (float)g.px, pixy = (float)g.py;
@@ -170,12 +162,10 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : GSR_FWD_MIN_CTAS) k_render_fw
             if (k + lane < cnt) {
                 const float4 a = s_r0[k + lane];
                 hit = subtile_hit(g, a.x, a.y, a.w);
-#ifndef GSR_NO_ELLIPSE_CULL
                 if (hit) {
                     const float4 co = s_r1[k + lane];
                     hit = subtile_hit_ellipse(g, a.x, a.y, co.x, co.y, co.z, s_r2[k + lane].w);
                 }
-#endif
             }
             unsigned m = __ballot_sync(kFull, hit);
             unsigned blended = 0u;
@@ -234,15 +224,15 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : GSR_FWD_MIN_CTAS) k_render_fw
     }
 }
 
-void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
+void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
                        uint8_t* contrib, const float* extra, float* out_extra, cudaStream_t s)
 {
     if (extra != nullptr)
-        k_render_fwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+        k_render_fwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
                                                    out_color, contrib, extra, out_extra);
     else
-        k_render_fwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+        k_render_fwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
                                                     out_color, contrib, nullptr, nullptr);
 }
 
@@ -256,12 +246,8 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-#ifndef GSR_BWD_MIN_CTAS
-#define GSR_BWD_MIN_CTAS 5
-#endif
 template <bool EXTRA>
-__global__ void __launch_bounds__(256, EXTRA ? 4 : GSR_BWD_MIN_CTAS) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
-                                                    const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256, EXTRA ? 4 : kBwdMinCtas) k_render_bwd(int W, int H, int gx, const uint2* __restrict__ ranges,
                                                     const uint32_t* __restrict__ point_list,
                                                     const float4* __restrict__ rec, const float* __restrict__ bg,
                                                     const float* __restrict__ final_T,
@@ -281,7 +267,7 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : GSR_BWD_MIN_CTAS) k_render_bw
     __shared__ uint8_t s_cb[kBatch];     // forward's contribution byte: bit w <=> warp w blended this entry
     __shared__ uint32_t s_max;
 
-    const int tile = GSR_TILE_OF_BLOCK;
+    const int tile = ((int)blockIdx.x);
     const TileGeom g = tile_geom(tile, gx, W, H);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float pixx = (float)g.px, pixy = (float)g.py;
@@ -460,18 +446,18 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : GSR_BWD_MIN_CTAS) k_render_bw
     }
 }
 
-void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* order, const uint32_t* point_list,
+void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
                        const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
                        float* dL_dopacity, float* dL_dcolors, const float* extra, const float* dL_dpix_extra,
                        float* dL_dextra, cudaStream_t s)
 {
     if (extra != nullptr)
-        k_render_bwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+        k_render_bwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
                                                    contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, extra,
                                                    dL_dpix_extra, dL_dextra);
     else
-        k_render_bwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, order, point_list, rec, bg, final_T, n_contrib,
+        k_render_bwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
                                                     contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, nullptr,
                                                     nullptr, nullptr);
 }
