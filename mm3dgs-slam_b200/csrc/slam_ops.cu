@@ -54,9 +54,9 @@ __device__ __forceinline__ bool loss_mask(int flags, const LossArgs& a, int pix,
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
-// Sum acc[0..n) over the CTA in a fixed order and store to out[0..n).
-template <int N>
-__device__ __forceinline__ void block_sum_store(double (&acc)[N], double* out, double (*s_red)[kLT / 32])
+// Sum acc[0..N) over a CTA of WARPS warps in a fixed order and store to out[0..N).
+template <int N, int WARPS>
+__device__ __forceinline__ void block_sum_store(const double (&acc)[N], double* out, double (*s_red)[WARPS])
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -70,13 +70,13 @@ __device__ __forceinline__ void block_sum_store(double (&acc)[N], double* out, d
     if (threadIdx.x < N) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kLT / 32; w++) v += s_red[threadIdx.x][w];
+        for (int w = 0; w < WARPS; w++) v += s_red[threadIdx.x][w];
         out[threadIdx.x] = v;
     }
 }
 
 // ---- pass 1: per-tile sums (+ the three SSIM derivative maps) ------------------------------------------
-__global__ void __launch_bounds__(kLT) k_loss_fwd(const LossArgs a)
+__global__ void __launch_bounds__(kLT, 5) k_loss_fwd(const LossArgs a)
 {
     __shared__ float s_x[kPH][kPW], s_y[kPH][kPW];
     __shared__ float s_h[5][kPH][kTW];
@@ -85,11 +85,10 @@ __global__ void __launch_bounds__(kLT) k_loss_fwd(const LossArgs a)
     const int tid = threadIdx.x, z = blockIdx.z;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const int cta = (z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    double acc[kNPart];
-#pragma unroll
-    for (int j = 0; j < kNPart; j++) acc[j] = 0.0;
 
     if (z < 3) {
+        // a thread sees at most two pixels: plain floats here, fp64 from the CTA reduction on
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
         const float* X = a.image + (size_t)z * HW;
         const float* Y = a.gt_color + (size_t)z * HW;
         if (a.c.color_mode == GSR_COLOR_L1_SSIM) {
@@ -112,17 +111,29 @@ __global__ void __launch_bounds__(kLT) k_loss_fwd(const LossArgs a)
                 s_h[0][r][c] = m1; s_h[1][r][c] = m2; s_h[2][r][c] = e11; s_h[3][r][c] = e22; s_h[4][r][c] = e12;
             }
             __syncthreads();
-            for (int i = tid; i < kTH * kTW; i += kLT) {
-                const int r = i / kTW, c = i - r * kTW;
+            // vertical pass: a thread owns one column and two ADJACENT rows, so the 12 staged rows it reads serve both
+            static_assert(kTH * kTW == 2 * kLT, "two output pixels per thread");
+            const int c = tid & (kTW - 1), r0 = (tid / kTW) * 2;
+            float mo[2][5];
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int q = 0; q < 5; q++) mo[j][q] = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * kWR + 1; k++) {
+#pragma unroll
+                for (int q = 0; q < 5; q++) {
+                    const float h = s_h[q][r0 + k][c];
+                    if (k <= 2 * kWR) mo[0][q] += a.win.w[k] * h;
+                    if (k >= 1) mo[1][q] += a.win.w[k - 1] * h;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int r = r0 + j;
                 const int gx = x0 + c, gy = y0 + r;
                 if (gx >= W || gy >= H) continue;
-                float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
-#pragma unroll
-                for (int k = 0; k <= 2 * kWR; k++) {
-                    const float w = a.win.w[k];
-                    mu1 += w * s_h[0][r + k][c]; mu2 += w * s_h[1][r + k][c]; e11 += w * s_h[2][r + k][c];
-                    e22 += w * s_h[3][r + k][c]; e12 += w * s_h[4][r + k][c];
-                }
+                const float mu1 = mo[j][0], mu2 = mo[j][1], e11 = mo[j][2], e22 = mo[j][3], e12 = mo[j][4];
                 // R/utils/loss_utils.py:126-148
                 const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
                 const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
@@ -141,8 +152,8 @@ __global__ void __launch_bounds__(kLT) k_loss_fwd(const LossArgs a)
                     a.dmaps[(size_t)(1 * 3 + z) * HW + pix] = dS_dsig1;
                     a.dmaps[(size_t)(2 * 3 + z) * HW + pix] = dS_dsig12;
                 }
-                acc[0] += (double)fabsf(s_x[r + kWR][c + kWR] - s_y[r + kWR][c + kWR]);
-                acc[1] += (double)S;
+                acc0 += fabsf(s_x[r + kWR][c + kWR] - s_y[r + kWR][c + kWR]);
+                acc1 += S;
             }
         } else if (a.c.color_mode != GSR_COLOR_NONE) {
             for (int i = tid; i < kTH * kTW; i += kLT) {
@@ -151,12 +162,18 @@ __global__ void __launch_bounds__(kLT) k_loss_fwd(const LossArgs a)
                 if (gx >= W || gy >= H) continue;
                 const int pix = gy * W + gx;
                 if (loss_mask(a.c.color_mask, a, pix, HW)) {
-                    acc[0] += (double)fabsf(X[pix] - Y[pix]);
-                    acc[2] += 1.0;
+                    acc0 += fabsf(X[pix] - Y[pix]);
+                    acc2 += 1.f;
                 }
             }
         }
-    } else if (a.c.depth_mode != GSR_DEPTH_NONE) {
+        const double acc[3] = {(double)acc0, (double)acc1, (double)acc2};
+        block_sum_store<3, kLT / 32>(acc, a.partials + (size_t)cta * kNPart, s_red);
+    } else {
+        double acc[kNPart];
+#pragma unroll
+        for (int j = 0; j < kNPart; j++) acc[j] = 0.0;
+        if (a.c.depth_mode != GSR_DEPTH_NONE)
         for (int i = tid; i < kTH * kTW; i += kLT) {
             const int r = i / kTW, c = i - r * kTW;
             const int gx = x0 + c, gy = y0 + r;
@@ -173,26 +190,35 @@ __global__ void __launch_bounds__(kLT) k_loss_fwd(const LossArgs a)
                 acc[7] += y2; acc[8] += y2 * y2; acc[9] += x * y2;
             }
         }
+        block_sum_store<kNPart, kLT / 32>(acc, a.partials + (size_t)cta * kNPart, s_red);
     }
-    block_sum_store(acc, a.partials + (size_t)cta * kNPart, s_red);
 }
 
 // ---- pass 2: one CTA folds the partials in a fixed order and derives every scalar the gradient needs ------
-__global__ void __launch_bounds__(kLT) k_loss_finalize(const LossArgs a, int n_tiles)
+constexpr int kFinT = 1024;   // the finalize CTA: latency-bound walk over the partial records, so as wide as a CTA gets
+__global__ void __launch_bounds__(kFinT) k_loss_finalize(const LossArgs a, int n_tiles)
 {
-    __shared__ double s_red[kNPart][kLT / 32];
+    __shared__ double s_red[kNPart][kFinT / 32];
     __shared__ double s_sum[2][kNPart];
-    for (int cls = 0; cls < 2; cls++) {
-        const int first = cls == 0 ? 0 : 3 * n_tiles, count = cls == 0 ? 3 * n_tiles : n_tiles;
+    {   // colour records: 3 slots in use
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int i = threadIdx.x; i < 3 * n_tiles; i += kFinT) {
+            const double* p = a.partials + (size_t)i * kNPart;
+            acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2];
+        }
+        block_sum_store<3, kFinT / 32>(acc, s_sum[0], s_red);
+        __syncthreads();
+    }
+    {   // depth records
         double acc[kNPart];
 #pragma unroll
         for (int j = 0; j < kNPart; j++) acc[j] = 0.0;
-        for (int i = threadIdx.x; i < count; i += kLT) {
-            const double* p = a.partials + (size_t)(first + i) * kNPart;
+        for (int i = threadIdx.x; i < n_tiles; i += kFinT) {
+            const double* p = a.partials + (size_t)(3 * n_tiles + i) * kNPart;
 #pragma unroll
             for (int j = 0; j < kNPart; j++) acc[j] += p[j];
         }
-        block_sum_store(acc, s_sum[cls], s_red);
+        block_sum_store<kNPart, kFinT / 32>(acc, s_sum[1], s_red);
         __syncthreads();
     }
     if (threadIdx.x != 0) return;
@@ -293,19 +319,28 @@ __global__ void __launch_bounds__(kLT) k_loss_bwd(const LossArgs a)
                 s_h[0][r][c] = h0; s_h[1][r][c] = h1; s_h[2][r][c] = h2;
             }
             __syncthreads();
-            for (int i = tid; i < kTH * kTW; i += kLT) {
-                const int r = i / kTW, c = i - r * kTW;
-                const int gx = x0 + c, gy = y0 + r;
-                if (gx >= W || gy >= H) continue;
-                float cA = 0.f, cB = 0.f, cC = 0.f;
+            const int c = tid & (kTW - 1), r0 = (tid / kTW) * 2;   // one column, two adjacent rows (as in pass 1)
+            float co[2][3];
 #pragma unroll
-                for (int k = 0; k <= 2 * kWR; k++) {
-                    const float w = a.win.w[k];
-                    cA += w * s_h[0][r + k][c]; cB += w * s_h[1][r + k][c]; cC += w * s_h[2][r + k][c];
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) co[j][q] = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * kWR + 1; k++) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const float h = s_h[q][r0 + k][c];
+                    if (k <= 2 * kWR) co[0][q] += a.win.w[k] * h;
+                    if (k >= 1) co[1][q] += a.win.w[k - 1] * h;
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int gx = x0 + c, gy = y0 + r0 + j;
+                if (gx >= W || gy >= H) continue;
                 const int pix = gy * W + gx;
                 const float x = X[pix], y = Y[pix];
-                G[pix] = k_ssim * (cA + 2.f * x * cB + y * cC) + k_l1 * sgn(x - y);
+                G[pix] = k_ssim * (co[j][0] + 2.f * x * co[j][1] + y * co[j][2]) + k_l1 * sgn(x - y);
             }
         } else {
             for (int i = tid; i < kTH * kTW; i += kLT) {
@@ -467,7 +502,7 @@ int gsr_slam_loss(gsr_stream_t stream_, const gsr_loss_config* cfg, const float*
     const int tx = (cfg->width + kTW - 1) / kTW, ty = (cfg->height + kTH - 1) / kTH;
     const dim3 grid(tx, ty, 4);
     k_loss_fwd<<<grid, kLT, 0, stream>>>(a);
-    k_loss_finalize<<<1, kLT, 0, stream>>>(a, tx * ty);
+    k_loss_finalize<<<1, kFinT, 0, stream>>>(a, tx * ty);
     int launches = 2;
     if (want_grad) {
         k_loss_bwd<<<grid, kLT, 0, stream>>>(a);   // CTAs of an image without a gradient buffer return at once
