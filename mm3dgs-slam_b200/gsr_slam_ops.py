@@ -14,7 +14,7 @@ there is no CPU path.
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional, Sequence
+from typing import Dict
 
 import torch
 

@@ -16,7 +16,8 @@ imported in the build container and its outputs are committed as tests/golden/lo
 nor installed in this image (the reference pins no version: R/environment.yml lists it without one) — PARITY
 UNPINNED for that one function: `pearson_corrcoef` below restates the published definition
 (torchmetrics.functional.regression.pearson: mean/var/cov accumulated over the batch, corr = cov / sqrt(var_x var_y),
-clamped to [-1, 1]).
+clamped to [-1, 1]); tests/test_oracle_cpu.py checks it against scipy.stats.pearsonr, an independent implementation of
+the same coefficient.
 """
 from math import exp
 

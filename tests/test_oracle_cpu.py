@@ -66,3 +66,21 @@ def test_binning_invariants():
     behind = gs["means3D"][:, 2] <= 0.1
     assert int(pre["radii"][behind].abs().sum()) == 0
     assert not bool(torch.isin(b["point_list"], torch.nonzero(behind).reshape(-1)).any())
+
+
+def test_pearson_restatement_matches_scipy():
+    """oracle/loss_oracle.py::pearson_corrcoef restates torchmetrics' definition (not installed, no version pinned by
+    the reference); scipy.stats.pearsonr is an independent implementation of the same published coefficient."""
+    from scipy import stats
+
+    from oracle import loss_oracle as LO
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5000, generator=g, dtype=torch.float64) * 1.5 + 3.0
+    for y in (0.4 * x + torch.randn(5000, generator=g, dtype=torch.float64), -x + 0.1, 1 / (x.abs() + 200.0)):
+        r = float(LO.pearson_corrcoef(x, y))
+        assert abs(r - stats.pearsonr(x.numpy(), y.numpy())[0]) < 1e-12
+    # the loss wrapper: invert_estimate picks the smaller of the two variants (R/utils/loss_utils.py:54-58)
+    est = 1.0 / x.abs()
+    a = 1 - LO.pearson_corrcoef(-est, x)
+    b = 1 - LO.pearson_corrcoef(1 / (est + 200.0), x)
+    assert float(LO.pearson_loss(x, est, invert_estimate=True)) == float(min(a, b))
