@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — restatement of the reference's image losses in plain torch ops (differentiable
-by autograd, runs on CPU or on a CUDA device), used only as the checker for gsr_slam_loss and as the
-"reference composition" timed next to it in bench.py.  Never imported by the product.
+by autograd, runs on CPU or on a CUDA device), used only as the checker for gsr_slam_loss
+(tests/, __graft_entry__.smoke()).  Never imported by the product; bench.py restates the composition it times inline.
 
 Follows (R = /root/reference):
   l1_loss, l2_loss          R/utils/loss_utils.py:64-72
