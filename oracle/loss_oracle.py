@@ -3,9 +3,10 @@ by autograd, runs on CPU or on a CUDA device), used only as the checker for gsr_
 (tests/, __graft_entry__.smoke()).  Never imported by the product; bench.py restates the composition it times inline.
 
 Follows (R = /root/reference):
-  l1_loss, l2_loss          R/utils/loss_utils.py:64-72
-  gaussian / create_window  R/utils/loss_utils.py:98-112
-  ssim / _ssim              R/utils/loss_utils.py:114-154
+  l1_loss                   R/utils/loss_utils.py:64-68
+  window_1d                 R/utils/loss_utils.py:98-112  (gaussian / create_window)
+  ssim_map / ssim           R/utils/loss_utils.py:114-154 (evaluated separably: the reference's 2-D window is an outer
+                            product, so two 1-D passes give the same moments up to float rounding)
   pearson_loss              R/utils/loss_utils.py:43-61
   mapper composition        R/slam/mapper.py:832-887
   tracker composition       R/slam/tracker.py:104-144
@@ -19,43 +20,48 @@ UNPINNED for that one function: `pearson_corrcoef` below restates the published 
 clamped to [-1, 1]); tests/test_oracle_cpu.py checks it against scipy.stats.pearsonr, an independent implementation of
 the same coefficient.
 """
-from math import exp
-
 import torch
 import torch.nn.functional as F
 
 
-def l1_loss(network_output, gt, mask=None):
-    if mask is None:
-        return torch.abs(network_output - gt).mean()
-    return torch.abs(network_output - gt)[:, mask].mean()
+def l1_loss(rendered, target, mask=None):
+    """Mean absolute difference, optionally over the pixels selected by a [H,W] mask in every channel."""
+    diff = (rendered - target).abs()
+    return diff.mean() if mask is None else diff[:, mask].mean()
 
 
-def gaussian(window_size, sigma):
-    g = torch.tensor([exp(-((x - window_size // 2) ** 2) / float(2 * sigma ** 2)) for x in range(window_size)],
-                     dtype=torch.float32)
+def window_1d(size=11, sigma=1.5):
+    """The reference's 11-tap window: exp(-(x - 5)^2 / (2 sigma^2)) evaluated in double, stored as float32 and divided
+    by its float32 sum; its 2-D window is the outer product of this vector with itself."""
+    x = torch.arange(size, dtype=torch.float64) - size // 2
+    g = torch.exp(-(x * x) / (2.0 * sigma * sigma)).to(torch.float32)
     return g / g.sum()
 
 
-def create_window(window_size, channel):
-    w1 = gaussian(window_size, 1.5).unsqueeze(1)
-    w2 = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0)
-    return w2.expand(channel, 1, window_size, window_size).contiguous()
+def _blur(x, w):
+    """Zero-padded 'same' filtering of every channel with the separable window w (x) w."""
+    lead = x.dim() == 3
+    x4 = x.unsqueeze(0) if lead else x
+    c, r = x4.shape[1], w.numel() // 2
+    k = w.to(device=x4.device, dtype=x4.dtype)
+    y = F.conv2d(x4, k.view(1, 1, 1, -1).repeat(c, 1, 1, 1), padding=(0, r), groups=c)
+    y = F.conv2d(y, k.view(1, 1, -1, 1).repeat(c, 1, 1, 1), padding=(r, 0), groups=c)
+    return y.squeeze(0) if lead else y
 
 
-def ssim(img1, img2, window_size=11, size_average=True):
-    channel = img1.size(-3)
-    window = create_window(window_size, channel).to(img1.device).type_as(img1)
-    pad = window_size // 2
-    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
-    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
-    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
-    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
-    C1, C2 = 0.01 ** 2, 0.03 ** 2
-    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
-    return ssim_map.mean() if size_average else ssim_map.mean(1).mean(1).mean(1)
+def ssim_map(a, b, size=11):
+    """Per-pixel structural similarity of two images from their windowed first and second moments."""
+    w = window_1d(size)
+    m_a, m_b = _blur(a, w), _blur(b, w)
+    var_a = _blur(a * a, w) - m_a * m_a
+    var_b = _blur(b * b, w) - m_b * m_b
+    cov = _blur(a * b, w) - m_a * m_b
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    return ((2 * m_a * m_b + c1) * (2 * cov + c2)) / ((m_a * m_a + m_b * m_b + c1) * (var_a + var_b + c2))
+
+
+def ssim(a, b, window_size=11):
+    return ssim_map(a, b, window_size).mean()
 
 
 def pearson_corrcoef(preds, target):
