@@ -28,6 +28,22 @@ def test_header_symbols_exported(built_lib):
     assert lib.gsr_abi_version() == 3
 
 
+def test_headers_are_plain_c(tmp_path):
+    """include/*.h is the drop-in boundary: it must compile as strict C99 (and as C++) with no torch / CUDA types."""
+    import shutil
+    import subprocess
+    src = tmp_path / "hdr_check.c"
+    src.write_text('#include "gsrast_b200.h"\n#include "gsloss_b200.h"\n'
+                   "int main(void) { gsr_loss_config c; gsr_gaussians g; gsr_camera k; gsr_grads d;\n"
+                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 3 ? 0 : 1; }\n")
+    inc = os.path.join(ROOT, "include")
+    if shutil.which("gcc"):
+        subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                       check=True)
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+
+
 def test_struct_mirrors_match_c_layout(built_lib):
     import diff_gaussian_rasterization as dgr
     # 4 x int32 + 7 pointers + float + int32
