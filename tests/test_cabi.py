@@ -44,6 +44,23 @@ def test_headers_are_plain_c(tmp_path):
         subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
 
 
+def test_c_client_links_and_runs(built_lib, tmp_path):
+    """A plain C host (tests/c_client.c) links the library and drives the entry points that need no GPU: the
+    boundary is usable without Python or torch."""
+    import shutil
+    import subprocess
+    import pytest
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "c_client")
+    libdir = os.path.dirname(built_lib)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_client.c"), "-o", exe, "-L", libdir, "-lgsrast_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("abi 3 ")
+
+
 def test_struct_mirrors_match_c_layout(built_lib):
     import diff_gaussian_rasterization as dgr
     # 4 x int32 + 7 pointers + float + int32
