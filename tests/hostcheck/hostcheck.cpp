@@ -1,0 +1,93 @@
+// hostcheck.cpp — runs the product's per-Gaussian math (mm3dgs-slam_b200/csrc/gsr_math.cuh, the GSR_HD functions the
+// CUDA kernels call) on the CPU, so that tests/test_hostcheck.py can compare it with the oracle without a GPU.
+// Test infrastructure: compiled by the test with g++, never linked into the library.
+#include "gsr_math.cuh"
+
+using namespace gsr;
+
+extern "C" {
+
+// Forward of k_preprocess_fwd's per-Gaussian part: covariance from (scale, raw quaternion), projection, conic,
+// radius, tile rectangle; SH colour with the kernel's direction normalisation.  Outputs are zero for culled Gaussians.
+void hc_forward(int P, int deg, int M, const float* means, const float* scales, const float* rots, float mod,
+                const float* shs, const float* view, const float* proj, const float* campos, int W, int H, float tanfovx,
+                float tanfovy, int* radii, int* tiles, int* rect, float* depth, float* xy, float* conic, float* rgb,
+                int* clamp_bits)
+{
+    const float focal_x = W / (2.0f * tanfovx), focal_y = H / (2.0f * tanfovy);
+    const int gx = (W + GSR_TILE - 1) / GSR_TILE, gy = (H + GSR_TILE - 1) / GSR_TILE;
+    for (int i = 0; i < P; i++) {
+        const V3 p = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
+        const V3 sc = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+        const V4 q = {rots[4 * i], rots[4 * i + 1], rots[4 * i + 2], rots[4 * i + 3]};
+        float cov6[6];
+        cov3d_from_scale_rot(sc, mod, q, cov6);
+        const PreOut o = preprocess_one(p, cov6, view, proj, W, H, tanfovx, tanfovy, focal_x, focal_y, gx, gy);
+        radii[i] = o.radius;
+        tiles[i] = o.tiles;
+        rect[4 * i] = o.x0; rect[4 * i + 1] = o.y0; rect[4 * i + 2] = o.x1; rect[4 * i + 3] = o.y1;
+        depth[i] = o.depth;
+        xy[2 * i] = o.px; xy[2 * i + 1] = o.py;
+        conic[3 * i] = o.cx; conic[3 * i + 1] = o.cy; conic[3 * i + 2] = o.cz;
+        rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = 0.f;
+        clamp_bits[i] = 0;
+        if (o.radius > 0) {
+            V3 dir = {p.x - campos[0], p.y - campos[1], p.z - campos[2]};
+            const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+            dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
+            const V3 c = sh_to_rgb(deg, shs + (size_t)i * M * 3, dir);
+            clamp_bits[i] = (c.x < 0 ? 1 : 0) | (c.y < 0 ? 2 : 0) | (c.z < 0 ? 4 : 0);
+            rgb[3 * i] = fmaxf(c.x, 0.f); rgb[3 * i + 1] = fmaxf(c.y, 0.f); rgb[3 * i + 2] = fmaxf(c.z, 0.f);
+        }
+    }
+}
+
+// Covariance path of k_preprocess_bwd: dL/dconic -> dL/dcov3D, dL/dmean (through J and the view transform),
+// dL/dscale, dL/d(raw quaternion).  Only Gaussians with radii > 0 are touched.
+void hc_cov_backward(int P, const int* radii, const float* means, const float* scales, const float* rots, float mod,
+                     const float* view, int W, int H, float tanfovx, float tanfovy, const float* dconic, float* dcov,
+                     float* dmean, float* dscale, float* drot)
+{
+    const float focal_x = W / (2.0f * tanfovx), focal_y = H / (2.0f * tanfovy);
+    for (int i = 0; i < P; i++) {
+        for (int k = 0; k < 6; k++) dcov[6 * i + k] = 0.f;
+        for (int k = 0; k < 3; k++) dmean[3 * i + k] = dscale[3 * i + k] = 0.f;
+        for (int k = 0; k < 4; k++) drot[4 * i + k] = 0.f;
+        if (radii[i] <= 0) continue;
+        const V3 p = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
+        const V3 sc = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+        const V4 q = {rots[4 * i], rots[4 * i + 1], rots[4 * i + 2], rots[4 * i + 3]};
+        float cov6[6];
+        cov3d_from_scale_rot(sc, mod, q, cov6);
+        const Cov2DGrad g = cov2d_backward(p, cov6, focal_x, focal_y, tanfovx, tanfovy, view, dconic[3 * i],
+                                           dconic[3 * i + 1], dconic[3 * i + 2]);
+        for (int k = 0; k < 6; k++) dcov[6 * i + k] = g.dcov[k];
+        dmean[3 * i] = g.dmean.x; dmean[3 * i + 1] = g.dmean.y; dmean[3 * i + 2] = g.dmean.z;
+        V3 ds;
+        V4 dq;
+        cov3d_backward(sc, mod, q, g.dcov, ds, dq);
+        dscale[3 * i] = ds.x; dscale[3 * i + 1] = ds.y; dscale[3 * i + 2] = ds.z;
+        drot[4 * i] = dq.x; drot[4 * i + 1] = dq.y; drot[4 * i + 2] = dq.z; drot[4 * i + 3] = dq.w;
+    }
+}
+
+// SH path of k_preprocess_bwd: clamp-masked dL/dRGB -> dL/dsh and the view-direction part of dL/dmean.
+void hc_sh_backward(int P, int deg, int M, const int* radii, const int* clamp_bits, const float* means, const float* shs,
+                    const float* campos, const float* dcolors, float* dsh, float* dmean)
+{
+    for (int i = 0; i < P; i++) {
+        for (int k = 0; k < 3 * M; k++) dsh[(size_t)i * M * 3 + k] = 0.f;
+        for (int k = 0; k < 3; k++) dmean[3 * i + k] = 0.f;
+        if (radii[i] <= 0) continue;
+        const V3 d0 = {means[3 * i] - campos[0], means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2]};
+        const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
+        const V3 dir = {d0.x / len, d0.y / len, d0.z / len};
+        float dRGB[3];
+        for (int ch = 0; ch < 3; ch++) dRGB[ch] = ((clamp_bits[i] >> ch) & 1) ? 0.f : dcolors[3 * i + ch];
+        const V3 ddir = sh_backward(deg, shs + (size_t)i * M * 3, dir, dRGB, dsh + (size_t)i * M * 3);
+        const V3 dm = dnormvdv(d0, ddir);
+        dmean[3 * i] = dm.x; dmean[3 * i + 1] = dm.y; dmean[3 * i + 2] = dm.z;
+    }
+}
+
+}  // extern "C"
