@@ -12,32 +12,9 @@
 // stride-12 words).  One 48-byte record per Gaussian replaces the reference's five separate
 // arrays, and cov3D is never written (the backward recomputes it from scale/rotation).
 #include "preprocess_common.cuh"
+#include "gsr_cull.cuh"
 
 namespace gsr {
-
-// Conservative squared radius (pixels^2) outside of which the splat cannot reach alpha >= 1/255:
-//   alpha = o*exp(power) >= 1/255  =>  power >= -ln(255 o),   power <= -|d|^2 / (2 lam_max)
-//   =>  |d|^2 <= 2 lam_max ln(255 o).
-// 3% + 0.5 px^2 slack covers the rounding of the conic and of the power evaluation; for very large
-// splats (lam_max > 1000 px^2) the relative error of the evaluated power is no longer negligible
-// against that slack, so they are never culled (+inf).  Used only to SKIP work in the blend kernels;
-// it never changes which (pixel, splat) pairs contribute.
-__device__ __forceinline__ float cull_radius2(float lam_max, float opacity)
-{
-    if (!(lam_max <= 1000.f)) return __int_as_float(0x7f800000);
-    const float L = fmaxf(logf(255.f * opacity), 0.f);
-    return 2.06f * lam_max * L + 0.5f;   // NaN opacity -> NaN -> never culled (tests are !(d2 > r2))
-}
-// Threshold for the exact ellipse-vs-sub-tile test of the forward blend: the splat can only contribute
-// where q(d) = -power(d) <= ln(255 o); 3% + 0.02 slack covers the rounding of the conic and of the
-// power evaluation inside the circle above (|d|^2 <= 2.06*1000*5.6, conic entries <= 1/0.3).  The low
-// 3 mantissa bits are overwritten with the SH clamp flags by the caller, hence the extra 1e-5.
-__device__ __forceinline__ float cull_power(float lam_max, float opacity)
-{
-    if (!(lam_max <= 1000.f)) return __int_as_float(0x7f800000);
-    const float L = fmaxf(logf(255.f * opacity), 0.f);
-    return (1.03f * L + 0.02f) * 1.00001f;
-}
 
 // ----------------------------------------------------------------------------------------------
 // Forward

@@ -23,6 +23,7 @@
 //    butterfly (14 shuffles instead of 45) and leave as ONE fire-and-forget RED.ADD.F32 per
 //    (warp, splat, term) instead of one atomicAdd per (pixel, splat, term).
 #include "gsr_internal.cuh"
+#include "gsr_cull.cuh"
 
 namespace gsr {
 
@@ -52,39 +53,6 @@ __device__ __forceinline__ TileGeom tile_geom(int tile, int gx, int W, int H)
     g.sy1 = (float)(oy + 3);
     g.inside = g.px < W && g.py < H;
     return g;
-}
-
-// Conservative test: can a splat centred at (x,y) with cull radius^2 rc2 touch the sub-tile?
-// Written as !(d2 > rc2) so that a NaN radius never culls.
-__device__ __forceinline__ bool subtile_hit(const TileGeom& g, float x, float y, float rc2)
-{
-    const float dx = fmaxf(0.f, fmaxf(g.sx0 - x, x - g.sx1));
-    const float dy = fmaxf(0.f, fmaxf(g.sy0 - y, y - g.sy1));
-    return !(dx * dx + dy * dy > rc2);
-}
-
-// Exact (up to the slack folded into `lim`) test: does the ellipse {q(d) <= lim}, q(d) = 0.5 d^T Q d, reach
-// the sub-tile?  The minimum of the convex q over the rectangle is 0 if the centre is inside, else it
-// lies on the (at most two) edges facing the centre, where q is a 1-D quadratic with a closed-form
-// minimiser.  Written so that NaNs never cull.
-__device__ __forceinline__ bool subtile_hit_ellipse(const TileGeom& g, float cx, float cy, float A, float B, float C,
-                                                    float lim)
-{
-    const float lx = g.sx0 - cx, hx = g.sx1 - cx;   // rect in splat-centred coordinates
-    const float ly = g.sy0 - cy, hy = g.sy1 - cy;
-    const float ex = lx > 0.f ? lx : (hx < 0.f ? hx : 0.f);   // offset to the facing vertical edge (0: inside in x)
-    const float ey = ly > 0.f ? ly : (hy < 0.f ? hy : 0.f);
-    if (ex == 0.f && ey == 0.f) return true;
-    float qmin = __int_as_float(0x7f800000);
-    if (ex != 0.f) {
-        const float dy = fminf(hy, fmaxf(ly, __fdividef(-B * ex, C)));
-        qmin = 0.5f * (A * ex * ex + C * dy * dy) + B * ex * dy;
-    }
-    if (ey != 0.f) {
-        const float dx = fminf(hx, fmaxf(lx, __fdividef(-B * ey, A)));
-        qmin = fminf(qmin, 0.5f * (A * dx * dx + C * ey * ey) + B * dx * ey);
-    }
-    return !(qmin > lim);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -161,10 +129,10 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
             bool hit = false;
             if (k + lane < cnt) {
                 const float4 a = s_r0[k + lane];
-                hit = subtile_hit(g, a.x, a.y, a.w);
+                hit = subtile_hit(g.sx0, g.sx1, g.sy0, g.sy1, a.x, a.y, a.w);
                 if (hit) {
                     const float4 co = s_r1[k + lane];
-                    hit = subtile_hit_ellipse(g, a.x, a.y, co.x, co.y, co.z, s_r2[k + lane].w);
+                    hit = subtile_hit_ellipse(g.sx0, g.sx1, g.sy0, g.sy1, a.x, a.y, co.x, co.y, co.z, s_r2[k + lane].w);
                 }
             }
             unsigned m = __ballot_sync(kFull, hit);

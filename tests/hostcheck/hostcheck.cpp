@@ -1,7 +1,9 @@
 // hostcheck.cpp — runs the product's per-Gaussian math (mm3dgs-slam_b200/csrc/gsr_math.cuh, the GSR_HD functions the
 // CUDA kernels call) on the CPU, so that tests/test_hostcheck.py can compare it with the oracle without a GPU.
 // Test infrastructure: compiled by the test with g++, never linked into the library.
+#include "gsr_cull.cuh"
 #include "gsr_math.cuh"
+#include <string.h>
 
 using namespace gsr;
 
@@ -12,7 +14,7 @@ extern "C" {
 void hc_forward(int P, int deg, int M, const float* means, const float* scales, const float* rots, float mod,
                 const float* shs, const float* view, const float* proj, const float* campos, int W, int H, float tanfovx,
                 float tanfovy, int* radii, int* tiles, int* rect, float* depth, float* xy, float* conic, float* rgb,
-                int* clamp_bits)
+                int* clamp_bits, float* lam_max)
 {
     const float focal_x = W / (2.0f * tanfovx), focal_y = H / (2.0f * tanfovy);
     const int gx = (W + GSR_TILE - 1) / GSR_TILE, gy = (H + GSR_TILE - 1) / GSR_TILE;
@@ -31,6 +33,7 @@ void hc_forward(int P, int deg, int M, const float* means, const float* scales, 
         conic[3 * i] = o.cx; conic[3 * i + 1] = o.cy; conic[3 * i + 2] = o.cz;
         rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = 0.f;
         clamp_bits[i] = 0;
+        lam_max[i] = o.lam_max;
         if (o.radius > 0) {
             V3 dir = {p.x - campos[0], p.y - campos[1], p.z - campos[2]};
             const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
@@ -88,6 +91,54 @@ void hc_sh_backward(int P, int deg, int M, const int* radii, const int* clamp_bi
         const V3 dm = dnormvdv(d0, ddir);
         dmean[3 * i] = dm.x; dmean[3 * i + 1] = dm.y; dmean[3 * i + 2] = dm.z;
     }
+}
+
+// The work-skipping tests of the blend kernels (gsr_cull.cuh) against the reference's per-pixel rule
+// (CR/forward.cu:332-345): for every splat and every 8x4 sub-tile of the W x H image, if ANY pixel of the sub-tile
+// would blend the splat (power <= 0 and min(0.99, o exp(power)) >= 1/255), both tests must keep the pair.
+// Thresholds are built exactly as k_preprocess_fwd stores them (low 3 bits of the power threshold replaced by flags).
+// Returns the number of violations; stats[0] = pairs that contribute, stats[1] = pairs kept by the circle test,
+// stats[2] = pairs kept by circle + ellipse tests, stats[3] = all pairs examined.
+long long hc_cull_check(int n, const float* xy, const float* conic, const float* opacity, const float* lam_max, int W, int H,
+                        long long* stats)
+{
+    long long bad = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    for (int i = 0; i < n; i++) {
+        const float x = xy[2 * i], y = xy[2 * i + 1];
+        const float A = conic[3 * i], B = conic[3 * i + 1], C = conic[3 * i + 2], o = opacity[i];
+        const float rc2 = cull_radius2(lam_max[i], o);
+        float lim = cull_power(lam_max[i], o);
+        {   // the kernel stores SH clamp flags in the low 3 mantissa bits; worst case for the test is all flags clear
+            unsigned u;
+            memcpy(&u, &lim, 4);
+            u &= ~7u;
+            memcpy(&lim, &u, 4);
+        }
+        for (int sy = 0; sy < H; sy += 4)
+            for (int sx = 0; sx < W; sx += 8) {
+                bool contributes = false;
+                for (int py = sy; py < sy + 4 && !contributes; py++)
+                    for (int px = sx; px < sx + 8; px++) {
+                        const float dx = x - (float)px, dy = y - (float)py;
+                        const float power = -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy;
+                        if (power > 0.0f) continue;
+                        const float alpha = fminf(0.99f, o * expf(power));
+                        if (alpha < 1.0f / 255.0f) continue;
+                        contributes = true;
+                        break;
+                    }
+                const float sx0 = (float)sx, sx1 = (float)(sx + 7), sy0 = (float)sy, sy1 = (float)(sy + 3);
+                const bool h1 = subtile_hit(sx0, sx1, sy0, sy1, x, y, rc2);
+                const bool h2 = h1 && subtile_hit_ellipse(sx0, sx1, sy0, sy1, x, y, A, B, C, lim);
+                stats[3]++;
+                stats[0] += contributes;
+                stats[1] += h1;
+                stats[2] += h2;
+                if (contributes && !h2) bad++;
+            }
+    }
+    return bad;
 }
 
 }  // extern "C"

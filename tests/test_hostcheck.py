@@ -52,10 +52,10 @@ def test_forward_math_matches_oracle(hc, P, W, H, deg, seed, cam_index):
     view, proj = cam.viewmatrix.reshape(16).contiguous(), cam.projmatrix.reshape(16).contiguous()
     radii, tiles, bits = (torch.zeros(P, dtype=torch.int32) for _ in range(3))
     rect = torch.zeros(P, 4, dtype=torch.int32)
-    depth, xy, conic, rgb = torch.zeros(P), torch.zeros(P, 2), torch.zeros(P, 3), torch.zeros(P, 3)
+    depth, xy, conic, rgb, lam = torch.zeros(P), torch.zeros(P, 2), torch.zeros(P, 3), torch.zeros(P, 3), torch.zeros(P)
     hc.hc_forward(P, deg, M, _p(gs["means3D"]), _p(gs["scales"]), _p(gs["rotations"]), ctypes.c_float(1.0), _p(gs["shs"]),
                   _p(view), _p(proj), _p(cam.campos), W, H, ctypes.c_float(cam.tanfovx), ctypes.c_float(cam.tanfovy),
-                  _p(radii), _p(tiles), _p(rect), _p(depth), _p(xy), _p(conic), _p(rgb), _p(bits))
+                  _p(radii), _p(tiles), _p(rect), _p(depth), _p(xy), _p(conic), _p(rgb), _p(bits), _p(lam))
     pre = O.preprocess(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix, cam.campos, W, H, cam.tanfovx,
                        cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], deg)
     vis = pre["radii"] > 0
@@ -109,3 +109,51 @@ def test_backward_math_matches_oracle(hc, P, W, H, deg, seed, cam_index):
         assert rel(dmean, want["dL_dmeans3D"]) < 1e-4
     else:
         assert float(dmean.abs().max()) == 0.0 and float(want["dL_dmeans3D"].abs().max()) < 1e-12
+
+
+def _cull_check(hc, xy, conic, opac, lam, W, H):
+    n = xy.shape[0]
+    stats = (ctypes.c_longlong * 4)()
+    hc.hc_cull_check.restype = ctypes.c_longlong
+    bad = hc.hc_cull_check(n, _p(xy.contiguous()), _p(conic.contiguous()), _p(opac.contiguous()), _p(lam.contiguous()), W, H, stats)
+    return int(bad), [int(v) for v in stats]
+
+
+def test_culling_never_drops_a_contributing_pair(hc):
+    """The sub-tile tests of the forward blend (csrc/gsr_cull.cuh) only skip work: for every splat of a projected scene
+    and for adversarial synthetic splats (needle-thin, huge, nearly transparent, centred on sub-tile corners), a
+    sub-tile containing ANY pixel that passes the reference's per-pixel rule is kept."""
+    W, H = 160, 120
+    gs, cam = _scene(6000, W, H, 0, 3, 1)
+    pre = O.preprocess(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix, cam.campos, W, H, cam.tanfovx,
+                       cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], 0)
+    vis = pre["radii"] > 0
+    a, b, c = pre["conic_opacity"][vis, 0], pre["conic_opacity"][vis, 1], pre["conic_opacity"][vis, 2]
+    # lam_max of the 2-D covariance = 1 / smaller eigenvalue of the conic
+    mid = 0.5 * (a + c)
+    lam_min_conic = mid - torch.sqrt(torch.clamp(mid * mid - (a * c - b * b), min=0))
+    lam = (1.0 / lam_min_conic).float()
+    bad, st = _cull_check(hc, pre["xy"][vis].float(), pre["conic_opacity"][vis, :3].float(),
+                          pre["conic_opacity"][vis, 3].float(), lam, W, H)
+    assert bad == 0, (bad, st)
+    assert st[0] > 0 and st[2] < 0.25 * st[3]            # and it does skip: fewer than a quarter of all pairs are kept
+
+    g = torch.Generator().manual_seed(11)
+    n = 4000
+    # covariances with extreme anisotropy / size, random orientation; centres snapped near sub-tile corners half the time
+    l1 = torch.exp(torch.rand(n, generator=g) * 9.0 - 1.2)          # 0.3 .. 2400 px^2
+    l2 = l1 * torch.exp(-torch.rand(n, generator=g) * 7.0)          # ratio down to 1e-3
+    l2 = torch.clamp(l2, min=0.3)
+    th = torch.rand(n, generator=g) * 3.14159265
+    cs, sn = torch.cos(th), torch.sin(th)
+    sxx, syy, sxy = l1 * cs * cs + l2 * sn * sn, l1 * sn * sn + l2 * cs * cs, (l1 - l2) * cs * sn
+    det = sxx * syy - sxy * sxy
+    conic = torch.stack([syy / det, -sxy / det, sxx / det], -1).float()
+    lam = torch.maximum(l1, l2).float()
+    xy = torch.stack([torch.rand(n, generator=g) * (W + 40) - 20, torch.rand(n, generator=g) * (H + 40) - 20], -1)
+    snap = torch.rand(n, generator=g) < 0.5
+    corner = torch.stack([torch.round(xy[:, 0] / 8) * 8, torch.round(xy[:, 1] / 4) * 4], -1) + (torch.rand(n, 2, generator=g) - 0.5) * 1e-3
+    xy = torch.where(snap[:, None], corner, xy).float()
+    opac = torch.cat([torch.rand(n // 2, generator=g), 1.0 / 255.0 + torch.rand(n - n // 2, generator=g) * 0.02]).float()
+    bad, st = _cull_check(hc, xy, conic, opac, lam, W, H)
+    assert bad == 0, (bad, st)
