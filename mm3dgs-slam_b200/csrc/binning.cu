@@ -26,6 +26,7 @@
 // coalesced sweeps.  HBM traffic: 3 x 16 B per Gaussian for the depth sort + ~20 B per instance,
 // instead of the reference's ~150 B per instance (6 onesweep passes over 12-byte pairs).
 #include "gsr_internal.cuh"
+#include "gsr_math.cuh"
 
 namespace gsr {
 
@@ -266,8 +267,7 @@ __device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t
     }
     const uint32_t total = __shfl_sync(kFullMask, incl, 31);
     const uint32_t excl = incl - n_l;
-    // exact k / w for k*w < 2^32 (k < 2^20 instances per splat, w < 2^12): q = umulhi(k, ceil(2^32 / w))
-    const uint32_t magic = 0xffffffffu / (packed >> 20) + 1u;
+    const uint32_t magic = div_magic(packed >> 20);   // exact k / w by multiplication (gsr_math.cuh)
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
     for (uint32_t b = 0; b < total; b += 32) {
         const uint32_t i = b + lane;
@@ -283,7 +283,7 @@ __device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t
         if (valid) {
             const uint32_t k = i - s_excl;
             const uint32_t w = s_pk >> 20, x0 = s_pk & 1023u, y0 = (s_pk >> 10) & 1023u;
-            const uint32_t ry = (w == 1u) ? k : __umulhi(k, s_magic);
+            const uint32_t ry = div_by_magic(k, w, s_magic);
             const uint32_t rx = k - ry * w;
             tile = (y0 + ry) * (uint32_t)gx + x0 + rx;
         }

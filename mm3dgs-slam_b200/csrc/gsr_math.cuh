@@ -96,6 +96,19 @@ GSR_HD V4 xform4x4(const V3& p, const float* m)
 }
 
 // NDC -> pixel; the reference evaluates this in double (double literals), CR/auxiliary.h:41-44.
+// Exact k / w by multiplication, used to unflatten an instance index k into (row, column) of a w-wide tile
+// rectangle: q = umulhi(k, ceil(2^32 / w)) equals k / w whenever k * w < 2^32 (here k < 2^20 instances per splat,
+// w < 2^12 tiles).  w == 1 has no 32-bit magic (2^32) and is handled by the caller's fast path.
+GSR_HD uint32_t div_magic(uint32_t w) { return 0xffffffffu / w + 1u; }
+GSR_HD uint32_t div_by_magic(uint32_t k, uint32_t w, uint32_t magic)
+{
+#if defined(__CUDA_ARCH__)
+    return (w == 1u) ? k : __umulhi(k, magic);
+#else
+    return (w == 1u) ? k : (uint32_t)(((unsigned long long)k * magic) >> 32);
+#endif
+}
+
 GSR_HD float ndc2pix(float v, int S) { return (float)(((v + 1.0) * S - 1.0) * 0.5); }
 
 // Tile rectangle of a splat of integer radius r centred at p (CR/auxiliary.h:46-56).

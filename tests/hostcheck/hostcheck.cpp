@@ -141,4 +141,17 @@ long long hc_cull_check(int n, const float* xy, const float* conic, const float*
     return bad;
 }
 
+// Exhaustive check of the tile partition's division-by-multiplication (div_magic / div_by_magic): every rectangle
+// width w the API admits (tile grids up to 1023 wide) and every instance index k < w * max_h.
+long long hc_magic_div_check(int max_w, int max_h)
+{
+    long long bad = 0;
+    for (uint32_t w = 1; w <= (uint32_t)max_w; w++) {
+        const uint32_t magic = div_magic(w);
+        const uint32_t kmax = w * (uint32_t)max_h;
+        for (uint32_t k = 0; k < kmax; k++) bad += (div_by_magic(k, w, magic) != k / w);
+    }
+    return bad;
+}
+
 }  // extern "C"

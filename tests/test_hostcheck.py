@@ -157,3 +157,10 @@ def test_culling_never_drops_a_contributing_pair(hc):
     opac = torch.cat([torch.rand(n // 2, generator=g), 1.0 / 255.0 + torch.rand(n - n // 2, generator=g) * 0.02]).float()
     bad, st = _cull_check(hc, xy, conic, opac, lam, W, H)
     assert bad == 0, (bad, st)
+
+
+def test_tile_partition_division_is_exact(hc):
+    """k / w by multiplication (binning.cu's instance -> (row, column) unflattening) for every width and instance index
+    the API admits: tile grids are at most 1023 x 1023 (gsr_forward_preprocess rejects larger images)."""
+    hc.hc_magic_div_check.restype = ctypes.c_longlong
+    assert hc.hc_magic_div_check(1023, 1023) == 0
