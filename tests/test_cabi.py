@@ -61,6 +61,43 @@ def test_c_client_links_and_runs(built_lib, tmp_path):
     assert out.startswith("abi 3 ")
 
 
+def test_workspace_layouts_are_sane(built_lib):
+    """Workspace sizing is host arithmetic: offsets 256-byte aligned and increasing, sizes cover the documented
+    per-Gaussian / per-pixel / per-instance arrays, nothing overflows at the largest supported problem sizes."""
+    import diff_gaussian_rasterization as dgr
+    lib = dgr._lib
+    lib.gsr_geom_layout_of.restype = None
+    lib.gsr_img_layout_of.restype = None
+    lib.gsr_binning_layout_of.restype = None
+
+    class Img(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_size_t) for k in ("final_T", "n_contrib", "ranges", "total")]
+
+    class Bin(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_size_t) for k in ("point_list", "total")]
+
+    prev = 0
+    for P, W, H in [(0, 16, 16), (1, 1, 1), (1000, 320, 240), (1_000_000, 640, 480), (5_000_000, 1920, 1080),
+                    (50_000_000, 3840, 2160)]:
+        g = dgr._GeomLayout()
+        lib.gsr_geom_layout_of(ctypes.c_int32(P), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(g))
+        offs = [g.rec, g.rects, g.depth_keys, g.counters, g.sorted_ids]
+        assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and g.total % 256 == 0
+        assert g.total == lib.gsr_geom_ws_bytes(P, W, H) >= 48 * P + 8 * P + 4 * P + 16 * P    # record, rect, key, sort buffers
+        assert g.rects - g.rec >= 48 * P and g.depth_keys - g.rects >= 8 * P
+        assert g.total >= prev
+        prev = g.total
+        im = Img()
+        lib.gsr_img_layout_of(ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(im))
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        assert im.n_contrib - im.final_T >= 4 * W * H and im.ranges - im.n_contrib >= 4 * W * H
+        assert im.total == lib.gsr_img_ws_bytes(W, H) >= 8 * W * H + 8 * tiles
+    for R in (0, 1, 4_500_000, 3_000_000_000):          # R is 64-bit: 3e9 instances = 39 GB of lists, no wrap-around
+        b = Bin()
+        lib.gsr_binning_layout_of(ctypes.c_int64(R), ctypes.byref(b))
+        assert b.point_list == 0 and b.total == lib.gsr_binning_ws_bytes(R) >= 13 * R
+
+
 def test_struct_mirrors_match_c_layout(built_lib):
     import diff_gaussian_rasterization as dgr
     # 4 x int32 + 7 pointers + float + int32
