@@ -150,6 +150,32 @@ def test_python_surface_matches_reference(built_lib):
     assert hasattr(dgr.GaussianRasterizer, "markVisible")
 
 
+def test_error_behaviour_matches_reference(built_lib):
+    """Same exceptions, raised before any device work: plain Exception for the SH / colour and the scale+rotation /
+    covariance exclusivity checks (DGR/diff_gaussian_rasterization/__init__.py:191-195), RuntimeError for a mis-shaped
+    means3D (DGR/rasterize_points.cu:57-59)."""
+    import pytest
+    import torch
+
+    import diff_gaussian_rasterization as dgr
+    import gsr_synth as S
+    gs, cam, _, bg = S.make_scene(16, 32, 32)
+    rs = dgr.GaussianRasterizationSettings(32, 32, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.viewmatrix, cam.projmatrix,
+                                           0, cam.campos, False, False)
+    ras, m2 = dgr.GaussianRasterizer(rs), torch.zeros(16, 3)
+    sr = dict(scales=gs["scales"], rotations=gs["rotations"])
+    for kw in (dict(shs=gs["shs"], colors_precomp=torch.zeros(16, 3), **sr), dict(**sr)):
+        with pytest.raises(Exception, match="SHs or precomputed colors") as ei:
+            ras(means3D=gs["means3D"], means2D=m2, opacities=gs["opacities"], **kw)
+        assert type(ei.value) is Exception
+    for kw in (dict(shs=gs["shs"], scales=gs["scales"]), dict(shs=gs["shs"], cov3D_precomp=torch.zeros(16, 6), **sr)):
+        with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance") as ei:
+            ras(means3D=gs["means3D"], means2D=m2, opacities=gs["opacities"], **kw)
+        assert type(ei.value) is Exception
+    with pytest.raises(RuntimeError, match=r"means3D must have dimensions \(num_points, 3\)"):
+        ras(means3D=torch.zeros(16, 4), means2D=m2, opacities=gs["opacities"], shs=gs["shs"], **sr)
+
+
 def test_no_cpu_fallback(built_lib):
     """CPU tensors are rejected loudly, never silently rendered on the host."""
     import pytest
