@@ -144,35 +144,72 @@ def slam_loss(cfg: dict, image, depth_image, gt_color, depth_target=None, gt_dep
 class FlatAdam:
     """`params`: dict name -> tensor; the tensors are re-homed as views of ONE flat fp32 buffer (`self.flat`, same
     order), so that parameters, gradients (a GradBucket-style flat tensor with the same layout) and both Adam moments
-    are four parallel arrays and a step is one kernel launch.  `lrs`: dict name -> learning rate (host floats; update
+    are four parallel arrays and a step is one kernel launch.  `prune` / `extend` are the reference's optimizer surgery
+    (_prune_optimizer / cat_tensors_to_optimizer) on those arrays.  `lrs`: dict name -> learning rate (host floats; update
     `self.lrs[name]` between steps for a schedule, R/slam/gaussian_model.py:196-202)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15):
         if len(params) > ADAM_MAX_SEGMENTS:
             raise ValueError(f"at most {ADAM_MAX_SEGMENTS} parameter groups")
-        first = next(iter(params.values()))
-        if not first.is_cuda:
-            raise RuntimeError("FlatAdam: CUDA tensors only (there is no CPU path)")
         self.names = list(params.keys())
-        n = sum(p.numel() for p in params.values())
-        self.flat = torch.empty(n, dtype=torch.float32, device=first.device)
-        self.views: Dict[str, torch.Tensor] = {}
-        ends, off = [], 0
-        for k, p in params.items():
-            v = self.flat[off: off + p.numel()].view(p.shape)
-            v.copy_(p.detach())
-            self.views[k] = v
-            off += p.numel()
-            ends.append(off)
-        self.seg_end = (ctypes.c_int64 * len(ends))(*ends)
         self.lrs = dict(lrs)
         self.beta1, self.beta2 = float(betas[0]), float(betas[1])
         self.eps = float(eps)
-        self.exp_avg = torch.zeros_like(self.flat)
-        self.exp_avg_sq = torch.zeros_like(self.flat)
         self.steps = 0
+        self._rehome({k: p.detach() for k, p in params.items()}, None, None)
+
+    def _rehome(self, params, exp_avg, exp_avg_sq):
+        """(Re)build the three flat buffers from per-group tensors (construction and map surgery; bookkeeping only —
+        the optimizer arithmetic is gsr_adam_step's)."""
+        first = next(iter(params.values()))
+        n = sum(p.numel() for p in params.values())
+        self.flat = torch.empty(n, dtype=torch.float32, device=first.device)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=first.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=first.device)
+        self.views = {}
+        ends, off = [], 0
+        for k in self.names:
+            p = params[k]
+            sl = slice(off, off + p.numel())
+            self.views[k] = self.flat[sl].view(p.shape)
+            self.views[k].copy_(p)
+            if exp_avg is not None:
+                self.exp_avg[sl].view(p.shape).copy_(exp_avg[k])
+                self.exp_avg_sq[sl].view(p.shape).copy_(exp_avg_sq[k])
+            off += p.numel()
+            ends.append(off)
+        self.seg_end = (ctypes.c_int64 * len(ends))(*ends)
+        return self.views
+
+    def _group_views(self, flat):
+        out, off = {}, 0
+        for k in self.names:
+            v = self.views[k]
+            out[k] = flat[off: off + v.numel()].view(v.shape)
+            off += v.numel()
+        return out
+
+    def prune(self, keep: torch.Tensor):
+        """Keep the rows (dim 0 of every group) selected by the bool mask `keep`, parameters and both moments alike
+        (_prune_optimizer, R/slam/gaussian_model.py:380-399; the mapper calls it with ~prune_mask).  The step count is
+        kept.  Returns the new parameter views — the old ones are stale, as the reference's old Parameters are."""
+        m, v = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        return self._rehome({k: self.views[k][keep] for k in self.names}, {k: m[k][keep] for k in self.names},
+                            {k: v[k][keep] for k in self.names})
+
+    def extend(self, new: Dict[str, torch.Tensor]):
+        """Append rows to every group; their moments start at zero and they share the running step count
+        (cat_tensors_to_optimizer, R/slam/gaussian_model.py:418-451).  Returns the new parameter views."""
+        m, v = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        cat = {k: torch.cat((self.views[k], new[k].detach().to(self.flat)), 0) for k in self.names}
+        return self._rehome(cat, {k: torch.cat((m[k], torch.zeros_like(new[k], dtype=torch.float32, device=self.flat.device)), 0)
+                                  for k in self.names},
+                            {k: torch.cat((v[k], torch.zeros_like(new[k], dtype=torch.float32, device=self.flat.device)), 0)
+                             for k in self.names})
 
     def step(self, flat_grads: torch.Tensor, grad_scale: float = 1.0, zero_grads: bool = False):
+        if not self.flat.is_cuda:
+            raise RuntimeError("FlatAdam.step: CUDA tensors only (there is no CPU path)")
         if flat_grads.numel() != self.flat.numel() or flat_grads.dtype != torch.float32 or not flat_grads.is_contiguous() \
                 or flat_grads.device != self.flat.device:
             raise RuntimeError("FlatAdam.step: gradient bucket must be a contiguous fp32 CUDA tensor of the parameter size")

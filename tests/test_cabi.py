@@ -120,7 +120,7 @@ def test_slam_ops_reject_cpu_tensors_and_bad_arguments(built_lib):
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.slam_loss(ops.mapper_splatam(), img, img, img, img[0], img[0])
     with pytest.raises(RuntimeError, match="CUDA"):
-        ops.FlatAdam({"a": torch.zeros(4)}, {"a": 1e-3})
+        ops.FlatAdam({"a": torch.zeros(4)}, {"a": 1e-3}).step(torch.zeros(4))      # bookkeeping may live anywhere, the step not
     lib = ctypes.CDLL(built_lib)
     lib.gsr_slam_loss_ws_bytes.restype = ctypes.c_size_t
     assert lib.gsr_slam_loss_ws_bytes(640, 480) >= 9 * 640 * 480 * 4
@@ -198,3 +198,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt, os.path.join(d, f)
+
+
+def test_flat_adam_surgery_matches_reference_optimizer_surgery(built_lib):
+    """FlatAdam.prune / .extend against the reference's _prune_optimizer / cat_tensors_to_optimizer semantics
+    (R/slam/gaussian_model.py:380-451) carried out on a torch.optim.Adam: same parameters and the same moments row for
+    row, zeros for appended rows, step count untouched.  Pure bookkeeping, so it runs on CPU tensors."""
+    import torch
+
+    import gsr_slam_ops as ops
+    g = torch.Generator().manual_seed(0)
+    P, shapes = 50, {"xyz": (3,), "f_dc": (1, 3), "opacity": (1,), "scaling": (3,), "rotation": (4,)}
+    params = {k: torch.randn(P, *sh, generator=g) for k, sh in shapes.items()}
+    opt = ops.FlatAdam(params, {k: 1e-3 for k in shapes})
+    opt.steps = 7
+    opt.exp_avg.copy_(torch.randn(opt.flat.numel(), generator=g))
+    opt.exp_avg_sq.copy_(torch.rand(opt.flat.numel(), generator=g))
+    m0, v0 = ({k: t.clone() for k, t in opt._group_views(buf).items()} for buf in (opt.exp_avg, opt.exp_avg_sq))
+
+    keep = torch.rand(P, generator=g) < 0.6
+    views = opt.prune(keep)
+    n1 = int(keep.sum())
+    assert opt.steps == 7 and opt.flat.numel() == sum(v.numel() for v in views.values())
+    for k in shapes:
+        assert torch.equal(views[k], params[k][keep]) and views[k].shape == (n1,) + shapes[k]
+        assert torch.equal(opt._group_views(opt.exp_avg)[k], m0[k][keep])
+        assert torch.equal(opt._group_views(opt.exp_avg_sq)[k], v0[k][keep])
+        assert views[k].data_ptr() >= opt.flat.data_ptr() and views[k].is_contiguous()      # still views of the flat buffer
+
+    new = {k: torch.randn(9, *sh, generator=g) for k, sh in shapes.items()}
+    views = opt.extend(new)
+    for k in shapes:
+        assert torch.equal(views[k], torch.cat((params[k][keep], new[k]), 0))
+        assert torch.equal(opt._group_views(opt.exp_avg)[k], torch.cat((m0[k][keep], torch.zeros_like(new[k])), 0))
+        assert torch.equal(opt._group_views(opt.exp_avg_sq)[k], torch.cat((v0[k][keep], torch.zeros_like(new[k])), 0))
+    assert list(opt.seg_end) == [(n1 + 9) * c for c in (3, 6, 7, 10, 14)]
