@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 3
+#define GSR_ABI_VERSION 4
 
 typedef void* gsr_stream_t; /* cudaStream_t */
 
@@ -141,7 +141,11 @@ int gsr_forward_preprocess(gsr_stream_t stream, const gsr_gaussians* g, const gs
 
 /* Forward, phase 2: stable partition of the tile instances by tile in depth order (== the
  * reference's (tile|depth)-sorted list), tile ranges, per-tile front-to-back alpha compositing.
- * R must be the value phase 1 produced. */
+ * R is the CAPACITY of binning_ws in tile instances: either the value phase 1 produced, or — to keep the host from
+ * ever waiting on the GPU — any upper estimate chosen before phase 1 has finished (e.g. the previous frame's count
+ * plus a margin).  The kernels read the true count from the device; if it exceeds R they leave the outputs untouched
+ * (no out-of-bounds access), and the caller, who learns the true count from geom_ws + gsr_geom_layout.counters
+ * afterwards, repeats this call with a large enough workspace.  gsr_backward must be given the same R. */
 int gsr_forward_render(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* cam,
                        const int32_t* radii, int64_t R,
                        void* geom_ws, void* binning_ws, size_t binning_ws_bytes, void* img_ws,
@@ -173,8 +177,9 @@ typedef struct gsr_geom_layout {
     size_t rec;        /* float4[3P]: (px,py,depth,cull_r2) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
     size_t rects;      /* ushort4[P]: tile rectangle {x0,y0,x1,y1}, empty for culled Gaussians */
     size_t depth_keys; /* uint32[P]: float bits of the view depth, 0xFFFFFFFF for culled Gaussians */
-    size_t sorted_ids; /* uint32[P]: Gaussian ids in (depth, index) order, culled last */
-    size_t counters;   /* uint32[>=1]: [0] = R, the number of tile instances (valid after gsr_forward_preprocess) */
+    size_t sorted_ids; /* uint32[P]: the VISIBLE Gaussians' ids in (depth, index) order (counters[2] entries) */
+    size_t counters;   /* uint32[>=3]: [0] = R, the number of tile instances; [2] = number of visible Gaussians
+                        * (valid after gsr_forward_preprocess) */
     size_t total;
 } gsr_geom_layout;
 typedef struct gsr_img_layout { size_t final_T, n_contrib, ranges, total; } gsr_img_layout;

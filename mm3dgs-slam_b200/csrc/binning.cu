@@ -95,103 +95,83 @@ __device__ __forceinline__ void block_exclusive_scan(uint32_t* s_data, uint32_t*
 }
 
 // ================================================================================================
-// 1. Depth sort (P keys)
+// 1. Depth sort (visible Gaussians only)
 // ================================================================================================
-__global__ void __launch_bounds__(kSortThreads) k_digit_count(const uint32_t* __restrict__ keys, int n, int shift,
-                                                              uint32_t mask, uint32_t* __restrict__ hist)
-{
-    __shared__ uint32_t s_hist[kBins];
-    const int tid = threadIdx.x;
-    for (int b = tid; b < kBins; b += kSortThreads) s_hist[b] = 0;
-    __syncthreads();
-    const int base = blockIdx.x * kSortChunk;
-#pragma unroll
-    for (int j = 0; j < kSortItems; j++) {
-        const int i = base + j * kSortThreads + tid;
-        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & mask], 1u);
-    }
-    __syncthreads();
-    uint32_t* row = hist + (size_t)blockIdx.x * kBins;
-    for (int b = tid; b < kBins; b += kSortThreads) row[b] = s_hist[b];
-}
+// Three single-kernel LSD passes (11 / 11 / 10 bits) in the "onesweep" form: the three global digit histograms
+// are accumulated by k_preprocess_fwd while the key is still in a register, so a pass only has to rank its 4096-key
+// block locally (per-warp 16-bit counters, MATCH.ANY) and find how many keys with the same digit precede the block —
+// by decoupled look-back over the blocks' published per-digit counts instead of a count kernel + a column-scan
+// kernel.  Blocks take their index from a ticket counter, so every block a look-back waits on is already running.
+// Pass 0 drops the culled Gaussians (key 0xFFFFFFFF): passes 1 and 2 and the tile partition only see the visible ones.
+//
+// status[block][bin]: bits 31..29 tag, bits 28..0 count.  tag 2p+1 = block's own count for pass p, tag 2p+2 = inclusive
+// prefix over blocks 0..block; anything else = not published yet for this pass (the array is zeroed once per frame and
+// reused by the three passes).
+constexpr uint32_t kStatMask = 0x1fffffffu;
 
-// Column scan of H[chunks][bins]: in place H[c][b] <- sum_{c' < c} H[c'][b]; totals[b] <- sum_c H[c][b].
-// One CTA per 32 bins; the chunk axis is split into 32 segments handled by the 32 warps.
-constexpr int kScanSegs = 32;
-__global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
-                                                                uint32_t* __restrict__ totals)
-{
-    __shared__ uint32_t s_seg[kScanSegs][32];
-    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    const int b = blockIdx.x * 32 + lane;
-    const int per = (chunks + kScanSegs - 1) / kScanSegs;
-    const int c0 = min(seg * per, chunks), c1 = min(c0 + per, chunks);
-    uint32_t sum = 0;
-    if (b < bins)
-        for (int c = c0; c < c1; c++) sum += hist[(size_t)c * bins + b];
-    s_seg[seg][lane] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int s = 0; s < seg; s++) run += s_seg[s][lane];
-    if (b < bins) {
-        for (int c = c0; c < c1; c++) {
-            const size_t o = (size_t)c * bins + b;
-            const uint32_t v = hist[o];
-            hist[o] = run;
-            run += v;
-        }
-        if (seg == kScanSegs - 1) totals[b] = run;
-    }
-}
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
-// Stable scatter of one digit pass.  vals_in == nullptr means "value = element index" (first pass).
-__global__ void __launch_bounds__(kSortThreads, 2) k_digit_scatter(const uint32_t* __restrict__ keys_in,
-                                                                const uint32_t* __restrict__ vals_in, int n, int shift,
-                                                                uint32_t mask, const uint32_t* __restrict__ base,
-                                                                const uint32_t* __restrict__ totals,
-                                                                uint32_t* __restrict__ keys_out,
-                                                                uint32_t* __restrict__ vals_out)
+template <int PASS>
+__global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* __restrict__ keys_in,
+                                                               const uint32_t* __restrict__ vals_in, int n_in,
+                                                               const uint32_t* __restrict__ ghist, uint32_t* status,
+                                                               uint32_t* counters, uint32_t* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ vals_out)
 {
     extern __shared__ uint32_t s_dyn[];
-    uint32_t* s_start = s_dyn;                                                    // [kBins] absolute start of this CTA's run
+    uint32_t* s_start = s_dyn;                                                    // [kBins] destination of this block's first key per bin
     uint16_t (*s_cnt)[kBins] = reinterpret_cast<uint16_t (*)[kBins]>(s_dyn + kBins);  // [kSortWarps][kBins] per-warp counters
     __shared__ uint32_t s_scan[kSortWarps];
+    __shared__ uint32_t s_block;
+    constexpr int shift = 11 * PASS;
+    constexpr uint32_t mask = PASS == 2 ? 1023u : 2047u;
+    constexpr uint32_t tag_agg = (uint32_t)(2 * PASS + 1) << 29, tag_incl = (uint32_t)(2 * PASS + 2) << 29;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int b = tid; b < kBins; b += kSortThreads) s_start[b] = totals[b];
-    for (int i = tid; i < kSortWarps * kBins / 2; i += kSortThreads) (s_dyn + kBins)[i] = 0;
+    if (tid == 0) s_block = atomicAdd(&counters[kCntTicket + PASS], 1u);
+    for (int b = tid; b < kBins; b += kSortThreads) s_start[b] = ghist[PASS * kBins + b];
     __syncthreads();
-    block_exclusive_scan<kBins / kSortThreads>(s_start, s_scan);    // bin starts over the whole array
-    const uint32_t* row = base + (size_t)blockIdx.x * kBins;
-    for (int b = tid; b < kBins; b += kSortThreads) s_start[b] += row[b];
-    // (visibility of s_start to the other warps is covered by the barrier after the counting sweep)
+    const int block = (int)s_block;
+    const int n = PASS == 0 ? n_in : (int)counters[kCntVisible];
+    if (block * kSortChunk >= n) return;
 
     // each warp owns a contiguous sub-chunk; lanes hold consecutive elements of each 32-element batch
-    const int wbase = blockIdx.x * kSortChunk + warp * (kSortChunk / kSortWarps);
-    uint32_t key[kSortItems];
+    const int wbase = block * kSortChunk + warp * (kSortChunk / kSortWarps);
+    uint32_t key[kSortItems], val[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         const int i = wbase + j * 32 + lane;
-        key[j] = (i < n) ? keys_in[i] : 0u;
+        key[j] = (i < n) ? keys_in[i] : 0xffffffffu;
+        val[j] = (PASS == 0 || i >= n) ? (uint32_t)i : vals_in[i];
     }
-    // all matches first (independent of each other: eight MATCH.ANY in flight), then ONE dependent sweep over the
-    // per-warp counters that also leaves every element's rank inside the warp's sub-chunk in a register
+    {   // zero this warp's counters (4 KB) while the loads are in flight
+        uint4* z = reinterpret_cast<uint4*>(&s_cnt[warp][0]);
+#pragma unroll
+        for (int k = 0; k < kBins * 2 / 16 / 32; k++) z[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    block_exclusive_scan<kBins / kSortThreads>(s_start, s_scan);    // bin starts over the whole array (2 barriers inside)
+    if (PASS == 0 && block == 0 && tid == kSortThreads - 1)          // number of visible Gaussians, for the later passes
+        counters[kCntVisible] = s_start[kBins - 1] + ghist[kBins - 1];
+
+    // rank inside the warp's sub-chunk: all matches first (independent: eight MATCH.ANY in flight), then ONE dependent
+    // sweep over the warp's counters.  Pass 0 ranks only the visible keys (culled ones are dropped here).
     unsigned peers[kSortItems];
+    bool valid[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         const int i = wbase + j * 32 + lane;
-        const uint32_t d = (i < n) ? ((key[j] >> shift) & mask) : 0xffffffffu;
-        peers[j] = __match_any_sync(kFullMask, d);   // digits of random keys: hardware MATCH measured faster than ballots
+        valid[j] = (i < n) && (PASS != 0 || key[j] != 0xffffffffu);
+        const uint32_t d = valid[j] ? ((key[j] >> shift) & mask) : 0xffffffffu;
+        peers[j] = __match_any_sync(kFullMask, d);
     }
     uint32_t ofs[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
-        const int i = wbase + j * 32 + lane;
-        const bool valid = i < n;
         const uint32_t d = (key[j] >> shift) & mask;
         const int leader = __ffs(peers[j]) - 1;
         uint32_t old = 0;
-        if (valid && lane == leader) {
+        if (valid[j] && lane == leader) {
             old = s_cnt[warp][d];
             s_cnt[warp][d] = (uint16_t)(old + __popc(peers[j]));
         }
@@ -199,8 +179,12 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_digit_scatter(const uint32_
         __syncwarp();
     }
     __syncthreads();
-    // exclusive prefix over the warps, per bin (the counters now hold each warp's total per bin)
-    for (int b = tid; b < kBins; b += kSortThreads) {
+    // per bin: exclusive prefix over the warps (in place), block count -> publish -> look back -> destination base
+    uint32_t agg[kBins / kSortThreads], excl[kBins / kSortThreads];
+    uint32_t* my_status = status + (size_t)block * kBins;
+#pragma unroll
+    for (int k = 0; k < kBins / kSortThreads; k++) {
+        const int b = tid + k * kSortThreads;
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; w++) {
@@ -208,41 +192,79 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_digit_scatter(const uint32_
             s_cnt[w][b] = (uint16_t)run;
             run += t;
         }
+        agg[k] = run;
+        excl[k] = 0;
+        st_status(my_status + b, (block == 0 ? tag_incl : tag_agg) | run);
     }
+    if (block > 0) {
+        int prev[kBins / kSortThreads];
+        unsigned pending = (1u << (kBins / kSortThreads)) - 1u;
+#pragma unroll
+        for (int k = 0; k < kBins / kSortThreads; k++) prev[k] = block - 1;
+        while (pending) {
+            uint32_t v[kBins / kSortThreads];
+#pragma unroll
+            for (int k = 0; k < kBins / kSortThreads; k++)
+                v[k] = ((pending >> k) & 1u) ? ld_status(status + (size_t)prev[k] * kBins + tid + k * kSortThreads) : 0u;
+            bool stalled = false;
+#pragma unroll
+            for (int k = 0; k < kBins / kSortThreads; k++) {
+                if (!((pending >> k) & 1u)) continue;
+                const uint32_t tag = v[k] & ~kStatMask;
+                if (tag == tag_incl) {
+                    excl[k] += v[k] & kStatMask;
+                    pending &= ~(1u << k);
+                } else if (tag == tag_agg) {
+                    excl[k] += v[k] & kStatMask;
+                    prev[k]--;
+                } else {
+                    stalled = true;
+                }
+            }
+            if (stalled) __nanosleep(40);
+        }
+#pragma unroll
+        for (int k = 0; k < kBins / kSortThreads; k++)
+            st_status(my_status + tid + k * kSortThreads, tag_incl | (excl[k] + agg[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < kBins / kSortThreads; k++) s_start[tid + k * kSortThreads] += excl[k];
     __syncthreads();
-    // scatter: position = bin start of this CTA + elements of earlier warps + rank inside the warp
+    // scatter: position = bin start + keys of earlier blocks + keys of earlier warps + rank inside the warp
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
-        const int i = wbase + j * 32 + lane;
-        if (i < n) {
+        if (valid[j]) {
             const uint32_t d = (key[j] >> shift) & mask;
             const uint32_t pos = s_start[d] + s_cnt[warp][d] + ofs[j];
             keys_out[pos] = key[j];
-            vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
+            vals_out[pos] = val[j];
         }
     }
 }
 
-void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s)
+template <int PASS>
+static void launch_sort_pass(const uint32_t* kin, const uint32_t* vin, int P, SortWS& w, uint32_t* counters, uint32_t* kout,
+                             uint32_t* vout, cudaStream_t s)
+{
+    constexpr size_t smem = (size_t)kBins * 4 + (size_t)kSortWarps * kBins * 2;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(k_sort_pass<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev] = true;
+    }
+    k_sort_pass<PASS><<<sort_chunks(P), kSortThreads, smem, s>>>(kin, vin, P, w.ghist, w.status, counters, kout, vout);
+}
+
+// Requires counters / ghist / status zeroed and ghist filled (k_preprocess_fwd).  Result: w.keys_a / w.vals_a hold the
+// counters[kCntVisible] visible Gaussians in (depth, index) order.
+void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, uint32_t* counters, cudaStream_t s)
 {
     if (P <= 0) return;
-    const int C = sort_chunks(P);
-    const uint32_t* kin = depth_keys;
-    const uint32_t* vin = nullptr;
-    uint32_t* kout[3] = {w.keys_a, w.keys_b, w.keys_a};
-    uint32_t* vout[3] = {w.vals_a, w.vals_b, w.vals_a};
-    const int shifts[3] = {0, 11, 22};
-    const uint32_t masks[3] = {2047u, 2047u, 1023u};
-    const size_t smem = (size_t)kBins * 4 + (size_t)kSortWarps * kBins * 2;
-    cudaFuncSetAttribute(k_digit_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int p = 0; p < 3; p++) {
-        k_digit_count<<<C, kSortThreads, 0, s>>>(kin, P, shifts[p], masks[p], w.hist);
-        k_column_scan<<<kBins / 32, 32 * kScanSegs, 0, s>>>(w.hist, C, kBins, w.totals);
-        k_digit_scatter<<<C, kSortThreads, smem, s>>>(kin, vin, P, shifts[p], masks[p], w.hist, w.totals, kout[p], vout[p]);
-        kin = kout[p];
-        vin = vout[p];
-    }
-    // result: w.keys_a / w.vals_a (depth-ordered keys and Gaussian ids)
+    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.keys_a, w.vals_a, s);
+    launch_sort_pass<1>(w.keys_a, w.vals_a, P, w, counters, w.keys_b, w.vals_b, s);
+    launch_sort_pass<2>(w.keys_b, w.vals_b, P, w, counters, w.keys_a, w.vals_a, s);
 }
 
 // ================================================================================================
@@ -306,6 +328,37 @@ __device__ __forceinline__ void load_rect(const uint32_t* __restrict__ perm, con
     }
 }
 
+// Column scan of H[chunks][bins]: in place H[c][b] <- sum_{c' < c} H[c'][b]; totals[b] <- sum_c H[c][b].
+// One CTA per 32 bins; the chunk axis is split into 32 segments handled by the 32 warps.
+constexpr int kScanSegs = 32;
+__global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
+                                                                uint32_t* __restrict__ totals,
+                                                                const uint32_t* __restrict__ counters, uint32_t cap)
+{
+    __shared__ uint32_t s_seg[kScanSegs][32];
+    if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const int per = (chunks + kScanSegs - 1) / kScanSegs;
+    const int c0 = min(seg * per, chunks), c1 = min(c0 + per, chunks);
+    uint32_t sum = 0;
+    if (b < bins)
+        for (int c = c0; c < c1; c++) sum += hist[(size_t)c * bins + b];
+    s_seg[seg][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int s = 0; s < seg; s++) run += s_seg[s][lane];
+    if (b < bins) {
+        for (int c = c0; c < c1; c++) {
+            const size_t o = (size_t)c * bins + b;
+            const uint32_t v = hist[o];
+            hist[o] = run;
+            run += v;
+        }
+        if (seg == kScanSegs - 1) totals[b] = run;
+    }
+}
+
 // Pass A.  A CTA owns a contiguous chunk of depth-ordered Gaussians.  It loads their tile rectangles,
 // scans the instance counts in shared memory and gives every warp an EQUAL share of the chunk's
 // instances (a share may start and end in the middle of a splat — a splat's tiles are distinct, so any
@@ -315,11 +368,14 @@ __device__ __forceinline__ void load_rect(const uint32_t* __restrict__ perm, con
 // (2) enumerates its instances ONCE, writing {tile, Gaussian id} records with coalesced 8-byte stores,
 // and (3) adds them to the CTA's tile histogram (row c of H).
 // Dynamic shared memory: uint32 s_hist[T], s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1].
-__global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict__ perm, int n, int per_cta,
+__global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict__ perm, int per_cta,
                                                     const ushort4* __restrict__ rects, int gx, int T,
                                                     uint32_t* __restrict__ hist, uint2* __restrict__ stream,
-                                                    uint2* __restrict__ segs, uint32_t* __restrict__ claim)
+                                                    uint2* __restrict__ segs, uint32_t* __restrict__ counters, uint32_t cap)
 {
+    if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
+    const int n = (int)counters[kCntVisible];          // the depth sort kept only the visible Gaussians
+    uint32_t* claim = counters + kCntClaim;
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_hist = s_dyn;
     uint32_t* s_id = s_dyn + T;
@@ -413,10 +469,12 @@ __global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict_
 // (A heaviest-tiles-first launch order for the blend kernels was tried here and measured no gain on scenes whose
 // tiles carry similar loads; the blend kernels take tiles in index order.)
 __global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict__ totals, int T, uint2* __restrict__ ranges,
-                                                      uint32_t* __restrict__ starts)
+                                                      uint32_t* __restrict__ starts, const uint32_t* __restrict__ counters,
+                                                      uint32_t cap)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
+    if (counters[kCntR] > cap) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -461,9 +519,11 @@ __device__ __forceinline__ unsigned tile_peers(uint32_t tile, bool valid, int tb
 // Dynamic shared memory: uint32 s_start[T]; uint16 s_cnt[nwarps][T].
 __global__ void __launch_bounds__(1024) k_tile_scatter(int T, const uint32_t* __restrict__ base,
                                                       const uint32_t* __restrict__ starts, uint2* __restrict__ stream,
-                                                      const uint2* __restrict__ segs, uint32_t* __restrict__ point_list)
+                                                      const uint2* __restrict__ segs, uint32_t* __restrict__ point_list,
+                                                      const uint32_t* __restrict__ counters, uint32_t cap)
 {
     extern __shared__ uint32_t s_dyn[];
+    if (counters[kCntR] > cap) return;
     uint32_t* s_start = s_dyn;
     uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + T);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -567,23 +627,28 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
     smem_scatter = (size_t)T * (4 + 2 * (size_t)(warps > 0 ? warps : 1));
 }
 
+// `cap`: number of instances the caller's stream / point_list arrays can hold.  If the scene has more (counters[kCntR],
+// known on the device only), every kernel here returns without touching them.
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s)
+                          uint2* stream, uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;
     int ctas, per_cta, warps;
     size_t smem_c, smem_s;
     tile_partition_plan(P, T, ctas, per_cta, warps, smem_c, smem_s);
     if (warps == 0 || smem_s > 220 * 1024 || smem_c > 220 * 1024 || per_cta > 65535) return -1;   // image / scene too large
-    if (smem_s > 48 * 1024 || smem_c > 48 * 1024) {   // opt in to the large B200 carve-out (per device, cheap host call)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {   // opt in to the large B200 carve-out once per device
         cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        configured[dev] = true;
     }
-    cudaMemsetAsync(claim, 0, sizeof(uint32_t), s);
-    k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, P, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, claim);
-    k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals);
-    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts);
-    k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list);
+    k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, counters, cap);
+    k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals, counters, cap);
+    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts, counters, cap);
+    k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list, counters, cap);
     return 0;
 }
 

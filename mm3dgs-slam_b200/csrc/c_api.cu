@@ -50,6 +50,19 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 }
 
 int api_fail(int code, const char* what, cudaError_t e) { return fail(code, what, e); }
+
+int device_sm_count()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 void api_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #define GSR_CUDA(expr)                                                     \
@@ -89,14 +102,16 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.rec = carve<float4>(p, n * 3);
     w.rects = carve<ushort4>(p, n);
     w.depth_keys = carve<uint32_t>(p, n);
+    // counters | ghist | status are contiguous: one memset zeroes them at the start of a forward
     w.counters = carve<uint32_t>(p, 64);
+    w.sort.ghist = carve<uint32_t>(p, 3 * 2048);
+    w.sort.status = carve<uint32_t>(p, (size_t)sort_chunks((int)n) * 2048);
+    w.zero_bytes = (size_t)(p - reinterpret_cast<char*>(w.counters));
     w.extra_gen = carve<float>(p, n * 3);
     w.sort.keys_a = carve<uint32_t>(p, n);
     w.sort.vals_a = carve<uint32_t>(p, n);
     w.sort.keys_b = carve<uint32_t>(p, n);
     w.sort.vals_b = carve<uint32_t>(p, n);
-    w.sort.hist = carve<uint32_t>(p, (size_t)sort_chunks((int)n) * 2048);
-    w.sort.totals = carve<uint32_t>(p, 2048);
     int ctas, per_cta, warps;
     size_t sc, ss;
     tile_partition_plan((int)n, T, ctas, per_cta, warps, sc, ss);
@@ -259,10 +274,11 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     a.scale_mod = g->scale_modifier; a.tanfovx = cam->tanfovx; a.tanfovy = cam->tanfovy;
     a.focal_y = H / (2.0f * cam->tanfovy);
     a.focal_x = W / (2.0f * cam->tanfovx);
-    a.radii = radii; a.rec = gw.rec; a.rects = gw.rects; a.depth_keys = gw.depth_keys; a.num_rendered = gw.counters;
+    a.radii = radii; a.rec = gw.rec; a.rects = gw.rects; a.depth_keys = gw.depth_keys; a.num_rendered = gw.counters + kCntR;
+    a.ghist = gw.sort.ghist;
     a.extra_gen = g->extra_mode == 1 ? gw.extra_gen : nullptr;
     prof_mark(ST_BEGIN, stream);
-    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, sizeof(uint32_t), stream));
+    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, gw.zero_bytes, stream));   // counters + digit histograms + look-back state
     launch_preprocess_fwd(a, stream);
     GSR_STAGE("preprocess", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS, stream, 1);
@@ -274,9 +290,9 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
         GSR_CUDA(cudaMemcpyAsync(hs.pinned, gw.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         GSR_CUDA(cudaEventRecord(hs.ev, stream));
     }
-    launch_depth_sort(gw.depth_keys, P, gw.sort, stream);
+    launch_depth_sort(gw.depth_keys, P, gw.sort, gw.counters, stream);
     GSR_STAGE("depth_sort", cam->debug, stream);
-    GSR_MARK(ST_DEPTH_SORT, stream, 9);
+    GSR_MARK(ST_DEPTH_SORT, stream, 3);
     if (async_r) {
         GSR_CUDA(cudaEventSynchronize(hs.ev));
         *num_rendered = *hs.pinned;
@@ -315,12 +331,14 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters + 1, bw.point_list, stream) != 0)
+    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters, (uint32_t)R,
+                              bw.point_list, stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 4);
     launch_render_fwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
-                      out_color, bw.contrib, g->extra_mode == 1 ? gw.extra_gen : g->extra_colors, out_extra, stream);
+                      out_color, bw.contrib, g->extra_mode == 1 ? gw.extra_gen : g->extra_colors, out_extra,
+                      gw.counters, (uint32_t)R, stream);
     GSR_STAGE("render", cam->debug, stream);
     GSR_MARK(ST_RENDER, stream, 1);
     return GSR_OK;

@@ -19,10 +19,16 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 //   rec[3i+2] = (r, g, b, bits)                 bits: SH clamp flags (bit ch set => channel clamped)
 // The reference keeps these in separate arrays (GeometryState, CR/rasterizer_impl.h:29-44) and
 // additionally stores cov3D (24 B) which the backward here recomputes from scale/rotation.
+// counters[] slots (device side; zeroed at the start of every forward together with ghist / status)
+constexpr int kCntR = 0;         // number of tile instances (num_rendered)
+constexpr int kCntClaim = 1;     // tile partition: next free slot of the instance stream
+constexpr int kCntVisible = 2;   // number of visible Gaussians (= length of the depth-sorted list)
+constexpr int kCntTicket = 3;    // [3] block tickets of the three depth-sort passes
+
 struct SortWS {
     uint32_t *keys_a, *vals_a, *keys_b, *vals_b;   // depth-sort ping-pong (P each); result in keys_a / vals_a
-    uint32_t* hist;                                // [sort_chunks(P)][2048]
-    uint32_t* totals;                              // [2048]
+    uint32_t* ghist;                               // [3][2048] global digit histograms of the visible depth keys
+    uint32_t* status;                              // [sort_chunks(P)][2048] look-back state of the sort passes
     uint32_t* tile_hist;                           // [partition CTAs][T]
     uint32_t* tile_totals;                         // [T]
     uint32_t* tile_starts;                         // [T]
@@ -32,7 +38,8 @@ struct GeomWS {
     float4* rec;
     ushort4* rects;        // tile rectangle {x0, y0, x1, y1}; empty for culled Gaussians
     uint32_t* depth_keys;  // float bits of the view depth; 0xFFFFFFFF for culled Gaussians
-    uint32_t* counters;    // [0] = R (number of tile instances)
+    uint32_t* counters;    // kCnt* slots
+    size_t zero_bytes;     // bytes from `counters` that must be zero when a forward starts (counters, ghist, status)
     float* extra_gen;      // [P,3] generated (z, 1, z^2) colours (extra_mode 1)
     SortWS sort;
     size_t total;
@@ -66,19 +73,21 @@ struct PreArgs {
     ushort4* rects;
     uint32_t* depth_keys;
     uint32_t* num_rendered;   // device counter, zeroed by the caller
+    uint32_t* ghist;          // [3][2048] digit histograms of the visible depth keys (11/11/10 bits), zeroed by the caller
     float* extra_gen;         // [P,3] generated depth/silhouette colours (z, 1, z^2), or nullptr
 };
 void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, const float* proj, uint8_t* present,
                          cudaStream_t s);
 
-void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, cudaStream_t s);
+void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, uint32_t* counters, cudaStream_t s);
 int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint2* stream, uint32_t* claim, uint32_t* point_list, cudaStream_t s);
+                          uint2* stream, uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s);
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
-                       uint8_t* contrib, const float* extra, float* out_extra, cudaStream_t s);
+                       uint8_t* contrib, const float* extra, float* out_extra, const uint32_t* counters, uint32_t cap,
+                       cudaStream_t s);
 void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, const float* final_T, const uint32_t* n_contrib,
                        const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
@@ -100,6 +109,8 @@ struct PreBwdArgs {
     const float* dL_dextra_gen;   // [P,3] gradient of the generated (z, 1, z^2) colours, or nullptr
 };
 void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
+
+int device_sm_count();   // SM count of the current device (cached per device)
 
 // ---- shared by the translation units that define extern "C" entry points (c_api.cu owns the state) ----
 int api_fail(int code, const char* what, cudaError_t e = cudaSuccess);   // records gsr_last_error(), returns code

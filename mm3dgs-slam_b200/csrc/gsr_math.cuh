@@ -263,187 +263,4 @@ GSR_HD PreOut preprocess_one(const V3& p, const float* cov6, const float* view, 
     return o;
 }
 
-// ------------------------------------------------------------------------------------------
-// Backward preprocessing of one Gaussian (CR/backward.cu:144-274 cov2D, :346-396 projection,
-// :20-139 SH, :278-341 scale/rotation).
-// ------------------------------------------------------------------------------------------
-
-// d/d(cov2D entries) -> dL/dcov3D[6] and the covariance-path part of dL/dmean.
-// Also returns dL/dT (2x3) and dL/dt for the camera-gradient extension.
-struct Cov2DGrad {
-    float dcov[6];
-    V3 dmean;      // W^T dL/dt
-    V3 dt;         // dL/dt (view-space mean)
-    float dT[2][3]; // dL/dT00..02, dL/dT10..12
-};
-
-GSR_HD Cov2DGrad cov2d_backward(const V3& mean, const float* cov6, float h_x, float h_y, float tanfovx,
-                                float tanfovy, const float* view, float dconx, float dcony, float dconz)
-{
-    Cov2DGrad g;
-    Cov2D c2 = cov2d_project(mean, h_x, h_y, tanfovx, tanfovy, cov6, view);
-    const M3& T = c2.T;
-    const V3 t = c2.t;
-    const float x_grad_mul = (c2.txtz < -c2.limx || c2.txtz > c2.limx) ? 0.f : 1.f;
-    const float y_grad_mul = (c2.tytz < -c2.limy || c2.tytz > c2.limy) ? 0.f : 1.f;
-    const float a = c2.a, b = c2.b, c = c2.c;
-    float denom = a * c - b * b;
-    float dL_da = 0, dL_db = 0, dL_dc = 0;
-    float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    if (denom2inv != 0) {
-        dL_da = denom2inv * (-c * c * dconx + 2 * b * c * dcony + (denom - a * c) * dconz);
-        dL_dc = denom2inv * (-a * a * dconz + 2 * a * b * dcony + (denom - a * c) * dconx);
-        dL_db = denom2inv * 2 * (b * c * dconx - (denom + 2 * b * b) * dcony + a * b * dconz);
-        g.dcov[0] = (T.c[0][0] * T.c[0][0] * dL_da + T.c[0][0] * T.c[1][0] * dL_db + T.c[1][0] * T.c[1][0] * dL_dc);
-        g.dcov[3] = (T.c[0][1] * T.c[0][1] * dL_da + T.c[0][1] * T.c[1][1] * dL_db + T.c[1][1] * T.c[1][1] * dL_dc);
-        g.dcov[5] = (T.c[0][2] * T.c[0][2] * dL_da + T.c[0][2] * T.c[1][2] * dL_db + T.c[1][2] * T.c[1][2] * dL_dc);
-        g.dcov[1] = 2 * T.c[0][0] * T.c[0][1] * dL_da + (T.c[0][0] * T.c[1][1] + T.c[0][1] * T.c[1][0]) * dL_db + 2 * T.c[1][0] * T.c[1][1] * dL_dc;
-        g.dcov[2] = 2 * T.c[0][0] * T.c[0][2] * dL_da + (T.c[0][0] * T.c[1][2] + T.c[0][2] * T.c[1][0]) * dL_db + 2 * T.c[1][0] * T.c[1][2] * dL_dc;
-        g.dcov[4] = 2 * T.c[0][2] * T.c[0][1] * dL_da + (T.c[0][1] * T.c[1][2] + T.c[0][2] * T.c[1][1]) * dL_db + 2 * T.c[1][1] * T.c[1][2] * dL_dc;
-    } else {
-        for (int i = 0; i < 6; i++) g.dcov[i] = 0;
-    }
-    // Sigma * rows of T
-    const float V00 = cov6[0], V01 = cov6[1], V02 = cov6[2], V11 = cov6[3], V12 = cov6[4], V22 = cov6[5];
-    const float s0x = T.c[0][0] * V00 + T.c[0][1] * V01 + T.c[0][2] * V02;
-    const float s0y = T.c[0][0] * V01 + T.c[0][1] * V11 + T.c[0][2] * V12;
-    const float s0z = T.c[0][0] * V02 + T.c[0][1] * V12 + T.c[0][2] * V22;
-    const float s1x = T.c[1][0] * V00 + T.c[1][1] * V01 + T.c[1][2] * V02;
-    const float s1y = T.c[1][0] * V01 + T.c[1][1] * V11 + T.c[1][2] * V12;
-    const float s1z = T.c[1][0] * V02 + T.c[1][1] * V12 + T.c[1][2] * V22;
-    g.dT[0][0] = 2 * s0x * dL_da + s1x * dL_db;
-    g.dT[0][1] = 2 * s0y * dL_da + s1y * dL_db;
-    g.dT[0][2] = 2 * s0z * dL_da + s1z * dL_db;
-    g.dT[1][0] = 2 * s1x * dL_dc + s0x * dL_db;
-    g.dT[1][1] = 2 * s1y * dL_dc + s0y * dL_db;
-    g.dT[1][2] = 2 * s1z * dL_dc + s0z * dL_db;
-    // T = W * J  ->  dL/dJ (non-zero entries); W.c[k][j] = view[4*j + k]
-    float dL_dJ00 = view[0] * g.dT[0][0] + view[4] * g.dT[0][1] + view[8] * g.dT[0][2];
-    float dL_dJ02 = view[2] * g.dT[0][0] + view[6] * g.dT[0][1] + view[10] * g.dT[0][2];
-    float dL_dJ11 = view[1] * g.dT[1][0] + view[5] * g.dT[1][1] + view[9] * g.dT[1][2];
-    float dL_dJ12 = view[2] * g.dT[1][0] + view[6] * g.dT[1][1] + view[10] * g.dT[1][2];
-    float tz = 1.f / t.z;
-    float tz2 = tz * tz;
-    float tz3 = tz2 * tz;
-    g.dt.x = x_grad_mul * -h_x * tz2 * dL_dJ02;
-    g.dt.y = y_grad_mul * -h_y * tz2 * dL_dJ12;
-    g.dt.z = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
-    // mean -> t is the 4x3 view transform: dL/dmean = W^T dL/dt
-    g.dmean.x = view[0] * g.dt.x + view[1] * g.dt.y + view[2] * g.dt.z;
-    g.dmean.y = view[4] * g.dt.x + view[5] * g.dt.y + view[6] * g.dt.z;
-    g.dmean.z = view[8] * g.dt.x + view[9] * g.dt.y + view[10] * g.dt.z;
-    return g;
-}
-
-// dL/d(scale), dL/d(raw quaternion) from dL/dcov3D[6] (CR/backward.cu:278-341).
-GSR_HD void cov3d_backward(const V3& scale, float mod, const V4& q, const float* dcov, V3& dscale, V4& dq)
-{
-    const float r = q.x, x = q.y, y = q.z, z = q.w;
-    // R in glm column-major: Rg.c[col][row]
-    M3 R = m3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                   2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                   2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-    const float sx = mod * scale.x, sy = mod * scale.y, sz = mod * scale.z;
-    M3 S = m3_cols(sx, 0.f, 0.f, 0.f, sy, 0.f, 0.f, 0.f, sz);
-    M3 M = m3_mul(S, R);
-    M3 dSig = m3_cols(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2],
-                      0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
-                      0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
-    M3 dM = m3_mul(M, dSig);
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) dM.c[j][i] *= 2.0f;
-    M3 Rt = m3_transpose(R);
-    M3 dMt = m3_transpose(dM);
-    dscale.x = Rt.c[0][0] * dMt.c[0][0] + Rt.c[0][1] * dMt.c[0][1] + Rt.c[0][2] * dMt.c[0][2];
-    dscale.y = Rt.c[1][0] * dMt.c[1][0] + Rt.c[1][1] * dMt.c[1][1] + Rt.c[1][2] * dMt.c[1][2];
-    dscale.z = Rt.c[2][0] * dMt.c[2][0] + Rt.c[2][1] * dMt.c[2][1] + Rt.c[2][2] * dMt.c[2][2];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        dMt.c[0][i] *= sx;
-        dMt.c[1][i] *= sy;
-        dMt.c[2][i] *= sz;
-    }
-    dq.x = 2 * z * (dMt.c[0][1] - dMt.c[1][0]) + 2 * y * (dMt.c[2][0] - dMt.c[0][2]) + 2 * x * (dMt.c[1][2] - dMt.c[2][1]);
-    dq.y = 2 * y * (dMt.c[1][0] + dMt.c[0][1]) + 2 * z * (dMt.c[2][0] + dMt.c[0][2]) + 2 * r * (dMt.c[1][2] - dMt.c[2][1]) - 4 * x * (dMt.c[2][2] + dMt.c[1][1]);
-    dq.z = 2 * x * (dMt.c[1][0] + dMt.c[0][1]) + 2 * r * (dMt.c[2][0] - dMt.c[0][2]) + 2 * z * (dMt.c[1][2] + dMt.c[2][1]) - 4 * y * (dMt.c[2][2] + dMt.c[0][0]);
-    dq.w = 2 * r * (dMt.c[0][1] - dMt.c[1][0]) + 2 * x * (dMt.c[2][0] + dMt.c[0][2]) + 2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
-}
-
-// d(normalize(v))/dv applied to dv (CR/auxiliary.h:106-116).
-GSR_HD V3 dnormvdv(const V3& v, const V3& dv)
-{
-    float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
-    float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    V3 o;
-    o.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
-    o.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
-    o.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
-    return o;
-}
-
-// SH backward for one Gaussian: writes dL/dsh (M float3) and returns dL/d(dir) (pre-normalisation
-// chain is applied by the caller).  dRGB must already be clamp-masked.  (CR/backward.cu:20-139)
-GSR_HD V3 sh_backward(int deg, const float* sh, const V3& dir, const float* dRGB, float* dsh)
-{
-#define SHV(k, ch) sh[3 * (k) + (ch)]
-#define DSH(k, ch) dsh[3 * (k) + (ch)]
-    const float x = dir.x, y = dir.y, z = dir.z;
-    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        const float g = dRGB[ch];
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        DSH(0, ch) = GSR_SH_C0 * g;
-        if (deg > 0) {
-            DSH(1, ch) = (-GSR_SH_C1 * y) * g;
-            DSH(2, ch) = (GSR_SH_C1 * z) * g;
-            DSH(3, ch) = (-GSR_SH_C1 * x) * g;
-            dx = -GSR_SH_C1 * SHV(3, ch);
-            dy = -GSR_SH_C1 * SHV(1, ch);
-            dz = GSR_SH_C1 * SHV(2, ch);
-            if (deg > 1) {
-                float xx = x * x, yy = y * y, zz = z * z;
-                float xy = x * y, yz = y * z, xz = x * z;
-                DSH(4, ch) = (GSR_SH_C2_0 * xy) * g;
-                DSH(5, ch) = (GSR_SH_C2_1 * yz) * g;
-                DSH(6, ch) = (GSR_SH_C2_2 * (2.f * zz - xx - yy)) * g;
-                DSH(7, ch) = (GSR_SH_C2_3 * xz) * g;
-                DSH(8, ch) = (GSR_SH_C2_4 * (xx - yy)) * g;
-                dx += GSR_SH_C2_0 * y * SHV(4, ch) + GSR_SH_C2_2 * 2.f * -x * SHV(6, ch) + GSR_SH_C2_3 * z * SHV(7, ch) + GSR_SH_C2_4 * 2.f * x * SHV(8, ch);
-                dy += GSR_SH_C2_0 * x * SHV(4, ch) + GSR_SH_C2_1 * z * SHV(5, ch) + GSR_SH_C2_2 * 2.f * -y * SHV(6, ch) + GSR_SH_C2_4 * 2.f * -y * SHV(8, ch);
-                dz += GSR_SH_C2_1 * y * SHV(5, ch) + GSR_SH_C2_2 * 2.f * 2.f * z * SHV(6, ch) + GSR_SH_C2_3 * x * SHV(7, ch);
-                if (deg > 2) {
-                    DSH(9, ch) = (GSR_SH_C3_0 * y * (3.f * xx - yy)) * g;
-                    DSH(10, ch) = (GSR_SH_C3_1 * xy * z) * g;
-                    DSH(11, ch) = (GSR_SH_C3_2 * y * (4.f * zz - xx - yy)) * g;
-                    DSH(12, ch) = (GSR_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g;
-                    DSH(13, ch) = (GSR_SH_C3_4 * x * (4.f * zz - xx - yy)) * g;
-                    DSH(14, ch) = (GSR_SH_C3_5 * z * (xx - yy)) * g;
-                    DSH(15, ch) = (GSR_SH_C3_6 * x * (xx - 3.f * yy)) * g;
-                    dx += (GSR_SH_C3_0 * SHV(9, ch) * 3.f * 2.f * xy + GSR_SH_C3_1 * SHV(10, ch) * yz +
-                           GSR_SH_C3_2 * SHV(11, ch) * -2.f * xy + GSR_SH_C3_3 * SHV(12, ch) * -3.f * 2.f * xz +
-                           GSR_SH_C3_4 * SHV(13, ch) * (-3.f * xx + 4.f * zz - yy) + GSR_SH_C3_5 * SHV(14, ch) * 2.f * xz +
-                           GSR_SH_C3_6 * SHV(15, ch) * 3.f * (xx - yy));
-                    dy += (GSR_SH_C3_0 * SHV(9, ch) * 3.f * (xx - yy) + GSR_SH_C3_1 * SHV(10, ch) * xz +
-                           GSR_SH_C3_2 * SHV(11, ch) * (-3.f * yy + 4.f * zz - xx) + GSR_SH_C3_3 * SHV(12, ch) * -3.f * 2.f * yz +
-                           GSR_SH_C3_4 * SHV(13, ch) * -2.f * xy + GSR_SH_C3_5 * SHV(14, ch) * -2.f * yz +
-                           GSR_SH_C3_6 * SHV(15, ch) * -3.f * 2.f * xy);
-                    dz += (GSR_SH_C3_1 * SHV(10, ch) * xy + GSR_SH_C3_2 * SHV(11, ch) * 4.f * 2.f * yz +
-                           GSR_SH_C3_3 * SHV(12, ch) * 3.f * (2.f * zz - xx - yy) + GSR_SH_C3_4 * SHV(13, ch) * 4.f * 2.f * xz +
-                           GSR_SH_C3_5 * SHV(14, ch) * (xx - yy));
-                }
-            }
-        }
-        ddx += dx * g;
-        ddy += dy * g;
-        ddz += dz * g;
-    }
-#undef SHV
-#undef DSH
-    V3 o = {ddx, ddy, ddz};
-    return o;
-}
-
 }  // namespace gsr

@@ -11,6 +11,7 @@
 // every thread then works on its own Gaussian out of conflict-free shared memory (stride-3 /
 // stride-12 words).  One 48-byte record per Gaussian replaces the reference's five separate
 // arrays, and cov3D is never written (the backward recomputes it from scale/rotation).
+#include "async_copy.cuh"
 #include "preprocess_common.cuh"
 #include "gsr_cull.cuh"
 
@@ -19,119 +20,208 @@ namespace gsr {
 // ----------------------------------------------------------------------------------------------
 // Forward
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPB, 5) k_preprocess_fwd(PreArgs a)
+// Persistent, TMA-fed: a CTA walks 256-Gaussian chunks; one thread asks the TMA unit for the next chunk's input
+// slices (cp.async.bulk -> the other shared-memory stage, completion on an mbarrier) before the CTA starts the math
+// of the current chunk, and the 12 KB of records leave as one bulk store.
+struct __align__(128) FwdIn {    // every member a multiple of 16 bytes
+    float means[kPB * 3];
+    float scales[kPB * 3];
+    float rots[kPB * 4];
+    float col[kPB * 3];          // SH (M == 1) or precomputed colours
+    float opac[kPB];
+};
+struct __align__(128) FwdOut {
+    float4 rec[kPB * 3];
+};
+constexpr size_t kFwdSmem = 2 * sizeof(FwdIn) + 2 * sizeof(FwdOut) + 64;
+
+__global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunks, int bulk_ok)
 {
-    __shared__ __align__(16) float s_means[kPB * 3];
-    __shared__ __align__(16) float s_scales[kPB * 3];
-    __shared__ __align__(16) float s_rots[kPB * 4];
-    __shared__ __align__(16) float s_col[kPB * 3];   // SH (M==1) or precomputed colours
-    __shared__ __align__(16) float4 s_rec[kPB * 3];
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    FwdIn* s_in = reinterpret_cast<FwdIn*>(s_raw);
+    FwdOut* s_out = reinterpret_cast<FwdOut*>(s_raw + 2 * sizeof(FwdIn));
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_raw + 2 * sizeof(FwdIn) + 2 * sizeof(FwdOut));
     __shared__ float s_cam[35];
     __shared__ uint32_t s_tiles;
 
     const int tid = threadIdx.x;
-    const int base = blockIdx.x * kPB;
-    const int nb = min(kPB, a.P - base);
     const bool has_sr = (a.cov3D_pre == nullptr);
     const bool sh_path = (a.colors == nullptr);
-    if (tid == 0) s_tiles = 0;
-
-    stage_in(a.means + (size_t)base * 3, s_means, nb * 3, tid);
-    if (has_sr) {
-        stage_in(a.scales + (size_t)base * 3, s_scales, nb * 3, tid);
-        stage_in(a.rots + (size_t)base * 4, s_rots, nb * 4, tid);
+    const bool col_staged = !sh_path || a.M == 1;
+    if (tid == 0) {
+        s_tiles = 0;
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        fence_mbar_init();
     }
-    if (!sh_path)
-        stage_in(a.colors + (size_t)base * 3, s_col, nb * 3, tid);
-    else if (a.M == 1)
-        stage_in(a.shs + (size_t)base * 3, s_col, nb * 3, tid);
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
     __syncthreads();
 
-    const int idx = base + tid;
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    int radius = 0, tiles = 0;
-    if (tid < nb) {
-        const float* view = s_cam;
-        const float* proj = s_cam + 16;
-        V3 p = {s_means[3 * tid], s_means[3 * tid + 1], s_means[3 * tid + 2]};
-        float cov6[6];
+    const uint32_t stage_bytes = (uint32_t)sizeof(float) * kPB * (3 + 1) + (has_sr ? (uint32_t)sizeof(float) * kPB * 7 : 0u) +
+                                 (col_staged ? (uint32_t)sizeof(float) * kPB * 3 : 0u);
+    auto is_bulk = [&](int c) { return bulk_ok && (c + 1) * kPB <= a.P; };
+    auto issue = [&](int c, int st) {   // tid 0 only
+        FwdIn& in = s_in[st];
+        const size_t b = (size_t)c * kPB;
+        mbar_arrive_expect_tx(&s_full[st], stage_bytes);
+        bulk_g2s(in.means, a.means + b * 3, sizeof(float) * kPB * 3, &s_full[st]);
+        bulk_g2s(in.opac, a.opac + b, sizeof(float) * kPB, &s_full[st]);
         if (has_sr) {
-            V3 sc = {s_scales[3 * tid], s_scales[3 * tid + 1], s_scales[3 * tid + 2]};
-            V4 q = {s_rots[4 * tid], s_rots[4 * tid + 1], s_rots[4 * tid + 2], s_rots[4 * tid + 3]};
-            cov3d_from_scale_rot(sc, a.scale_mod, q, cov6);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_pre[(size_t)idx * 6 + k];
+            bulk_g2s(in.scales, a.scales + b * 3, sizeof(float) * kPB * 3, &s_full[st]);
+            bulk_g2s(in.rots, a.rots + b * 4, sizeof(float) * kPB * 4, &s_full[st]);
         }
-        PreOut o = preprocess_one(p, cov6, view, proj, a.W, a.H, a.tanfovx, a.tanfovy, a.focal_x, a.focal_y,
-                                  a.gx, a.gy);
-        if (a.prefiltered) {
-            V3 pv = xform4x3(p, view);
-            if (pv.z <= 0.1f) {
-                printf("gsrast_b200: Gaussian %d culled although prefiltered is set\n", idx);
-                __trap();
+        if (col_staged) bulk_g2s(in.col, (sh_path ? a.shs : a.colors) + b * 3, sizeof(float) * kPB * 3, &s_full[st]);
+    };
+    if (tid == 0 && (int)blockIdx.x < nchunks && is_bulk(blockIdx.x)) issue(blockIdx.x, 0);
+
+    uint32_t my_tiles = 0;
+    int it = 0;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x, it++) {
+        const int st = it & 1;
+        FwdIn& in = s_in[st];
+        FwdOut& out = s_out[st];
+        const int base = c * kPB;
+        const int nb = min(kPB, a.P - base);
+        const int nxt = c + gridDim.x;
+        if (tid == 0 && nxt < nchunks && is_bulk(nxt)) issue(nxt, st ^ 1);
+        if (is_bulk(c)) {
+            mbar_wait(&s_full[st], (uint32_t)((it >> 1) & 1));
+        } else {   // ragged last chunk / unaligned arrays
+            stage_in(a.means + (size_t)base * 3, in.means, nb * 3, tid);
+            stage_in(a.opac + (size_t)base, in.opac, nb, tid);
+            if (has_sr) {
+                stage_in(a.scales + (size_t)base * 3, in.scales, nb * 3, tid);
+                stage_in(a.rots + (size_t)base * 4, in.rots, nb * 4, tid);
             }
+            if (col_staged) stage_in((sh_path ? a.shs : a.colors) + (size_t)base * 3, in.col, nb * 3, tid);
+            __syncthreads();
         }
-        radius = o.radius;
-        tiles = o.tiles;
-        if (radius > 0) {
-            float cr, cg, cb;
-            int bits = 0;
-            if (sh_path) {
-                V3 dir = {p.x - s_cam[32], p.y - s_cam[33], p.z - s_cam[34]};
-                float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-                dir.x = dir.x / len;
-                dir.y = dir.y / len;
-                dir.z = dir.z / len;
-                const float* sh = (a.M == 1) ? (s_col + 3 * tid) : (a.shs + (size_t)idx * a.M * 3);
-                V3 c = sh_to_rgb(a.D, sh, dir);
-                bits = (c.x < 0 ? 1 : 0) | (c.y < 0 ? 2 : 0) | (c.z < 0 ? 4 : 0);
-                cr = fmaxf(c.x, 0.0f);
-                cg = fmaxf(c.y, 0.0f);
-                cb = fmaxf(c.z, 0.0f);
+
+        const int idx = base + tid;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+        uint32_t dkey = 0xffffffffu;   // depth key of a visible Gaussian
+        if (tid < nb) {
+            const float* view = s_cam;
+            const float* proj = s_cam + 16;
+            V3 p = {in.means[3 * tid], in.means[3 * tid + 1], in.means[3 * tid + 2]};
+            float cov6[6];
+            if (has_sr) {
+                V3 sc = {in.scales[3 * tid], in.scales[3 * tid + 1], in.scales[3 * tid + 2]};
+                V4 q = {in.rots[4 * tid], in.rots[4 * tid + 1], in.rots[4 * tid + 2], in.rots[4 * tid + 3]};
+                cov3d_from_scale_rot(sc, a.scale_mod, q, cov6);
             } else {
-                cr = s_col[3 * tid];
-                cg = s_col[3 * tid + 1];
-                cb = s_col[3 * tid + 2];
+#pragma unroll
+                for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_pre[(size_t)idx * 6 + k];
             }
-            const float opacity = a.opac[idx];
-            r0 = make_float4(o.px, o.py, o.depth, cull_radius2(o.lam_max, opacity));
-            r1 = make_float4(o.cx, o.cy, o.cz, opacity);
-            // r2.w: power threshold for the sub-tile test, low 3 bits = SH clamp flags (read by the backward)
-            r2 = make_float4(cr, cg, cb, __int_as_float((__float_as_int(cull_power(o.lam_max, opacity)) & ~7) | bits));
+            PreOut o = preprocess_one(p, cov6, view, proj, a.W, a.H, a.tanfovx, a.tanfovy, a.focal_x, a.focal_y,
+                                      a.gx, a.gy);
+            if (a.prefiltered) {
+                V3 pv = xform4x3(p, view);
+                if (pv.z <= 0.1f) {
+                    printf("gsrast_b200: Gaussian %d culled although prefiltered is set\n", idx);
+                    __trap();
+                }
+            }
+            const int radius = o.radius;
+            my_tiles += (uint32_t)o.tiles;
+            if (radius > 0) {
+                float cr, cg, cb;
+                int bits = 0;
+                if (sh_path) {
+                    V3 dir = {p.x - s_cam[32], p.y - s_cam[33], p.z - s_cam[34]};
+                    float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+                    dir.x = dir.x / len;
+                    dir.y = dir.y / len;
+                    dir.z = dir.z / len;
+                    const float* sh = (a.M == 1) ? (in.col + 3 * tid) : (a.shs + (size_t)idx * a.M * 3);
+                    V3 cc = sh_to_rgb(a.D, sh, dir);
+                    bits = (cc.x < 0 ? 1 : 0) | (cc.y < 0 ? 2 : 0) | (cc.z < 0 ? 4 : 0);
+                    cr = fmaxf(cc.x, 0.0f);
+                    cg = fmaxf(cc.y, 0.0f);
+                    cb = fmaxf(cc.z, 0.0f);
+                } else {
+                    cr = in.col[3 * tid];
+                    cg = in.col[3 * tid + 1];
+                    cb = in.col[3 * tid + 2];
+                }
+                const float opacity = in.opac[tid];
+                r0 = make_float4(o.px, o.py, o.depth, cull_radius2(o.lam_max, opacity));
+                r1 = make_float4(o.cx, o.cy, o.cz, opacity);
+                // r2.w: power threshold for the sub-tile test, low 3 bits = SH clamp flags (read by the backward)
+                r2 = make_float4(cr, cg, cb, __int_as_float((__float_as_int(cull_power(o.lam_max, opacity)) & ~7) | bits));
+            }
+            a.radii[idx] = radius;
+            a.rects[idx] = radius > 0 ? make_ushort4((unsigned short)o.x0, (unsigned short)o.y0, (unsigned short)o.x1,
+                                                     (unsigned short)o.y1)
+                                      : make_ushort4(0, 0, 0, 0);
+            if (radius > 0) dkey = __float_as_uint(o.depth);
+            a.depth_keys[idx] = dkey;
+            if (a.extra_gen != nullptr) {   // SLAM depth / silhouette colours (z, 1, z^2); R/slam/renderer.py:26-43
+                const float z = radius > 0 ? o.depth : 0.f;
+                a.extra_gen[(size_t)idx * 3 + 0] = z;
+                a.extra_gen[(size_t)idx * 3 + 1] = radius > 0 ? 1.f : 0.f;
+                a.extra_gen[(size_t)idx * 3 + 2] = z * z;
+            }
         }
-        a.radii[idx] = radius;
-        a.rects[idx] = radius > 0 ? make_ushort4((unsigned short)o.x0, (unsigned short)o.y0, (unsigned short)o.x1,
-                                                 (unsigned short)o.y1)
-                                  : make_ushort4(0, 0, 0, 0);
-        a.depth_keys[idx] = radius > 0 ? __float_as_uint(o.depth) : 0xffffffffu;
-        if (a.extra_gen != nullptr) {   // SLAM depth / silhouette colours (z, 1, z^2); R/slam/renderer.py:26-43
-            const float z = radius > 0 ? o.depth : 0.f;
-            a.extra_gen[(size_t)idx * 3 + 0] = z;
-            a.extra_gen[(size_t)idx * 3 + 1] = radius > 0 ? 1.f : 0.f;
-            a.extra_gen[(size_t)idx * 3 + 2] = z * z;
+        {   // digit histograms of the depth sort (11 / 11 / 10 bits), while the key is in a register: fire-and-forget
+            // REDs; the low digits are mantissa bits (spread over 2048 addresses), the top digit (sign, exponent, one
+            // mantissa bit) takes a handful of values, so it is aggregated over the warp first
+            const bool v = dkey != 0xffffffffu;
+            if (v) {
+                atomicAdd(&a.ghist[dkey & 2047u], 1u);
+                atomicAdd(&a.ghist[2048u + ((dkey >> 11) & 2047u)], 1u);
+            }
+            const uint32_t d2 = v ? (dkey >> 22) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d2);
+            if (v && (tid & 31) == __ffs(peers) - 1) atomicAdd(&a.ghist[4096u + d2], (uint32_t)__popc(peers));
+        }
+        // the bulk store issued two iterations ago has finished reading this output stage
+        if (tid == 0) bulk_wait_read<1>();
+        __syncthreads();   // (also: every thread is done with the input stage)
+        out.rec[3 * tid + 0] = r0;
+        out.rec[3 * tid + 1] = r1;
+        out.rec[3 * tid + 2] = r2;
+        float4* dst = a.rec + (size_t)base * 3;
+        if (is_bulk(c)) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(dst, out.rec, sizeof(float4) * kPB * 3);
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < nb * 3; i += kPB) dst[i] = out.rec[i];
         }
     }
-    {   // R = total number of tile instances: warp reduce, one shared atomic per warp, one global per CTA
-        const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)tiles);
+    if (tid == 0) bulk_wait_read<0>();
+    {   // R = total number of tile instances: warp reduce, one shared atomic per warp, one global atomic per CTA
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_tiles);
         if ((tid & 31) == 0 && wsum) atomicAdd(&s_tiles, wsum);
+        __syncthreads();
+        if (tid == 0 && s_tiles) atomicAdd(a.num_rendered, s_tiles);
     }
-    s_rec[3 * tid + 0] = r0;
-    s_rec[3 * tid + 1] = r1;
-    s_rec[3 * tid + 2] = r2;
-    __syncthreads();
-    float4* out = a.rec + (size_t)base * 3;
-    for (int i = tid; i < nb * 3; i += kPB) out[i] = s_rec[i];
-    if (tid == 0 && s_tiles) atomicAdd(a.num_rendered, s_tiles);
 }
 
 void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return;
-    k_preprocess_fwd<<<(a.P + kPB - 1) / kPB, kPB, 0, s>>>(a);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(k_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        configured[dev] = true;
+    }
+    const int nchunks = (a.P + kPB - 1) / kPB;
+    const int grid = min(nchunks, 4 * device_sm_count());
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool col_staged = a.colors != nullptr || a.M == 1;
+    const int bulk_ok = al(a.means) && al(a.opac) && al(a.rec) && (a.cov3D_pre || (al(a.scales) && al(a.rots))) &&
+                        (!col_staged || al(a.colors ? a.colors : a.shs));
+    k_preprocess_fwd<<<grid, kPB, kFwdSmem, s>>>(a, nchunks, bulk_ok);
 }
 
 // present[i] = near-plane test only (CR/auxiliary.h:139-164 with prefiltered=false).

@@ -37,29 +37,20 @@ __device__ __forceinline__ void stage_in(const float* __restrict__ src, float* d
         for (int i = tid; i < n; i += kPB) dst[i] = ld_stream1(src + i);
     }
 }
-// Copy n contiguous floats shared -> global; ACC: add `old` (the accumulator's previous contents, staged into
-// shared memory at kernel start so that the read overlaps the math instead of sitting in front of the store).
+// Copy n contiguous floats shared -> global (ACC: add to what is there).  Only the ragged / unaligned chunks take
+// this path; full aligned chunks leave through the TMA unit (async_copy.cuh).
 template <bool ACC>
-__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, const float* old, int n, int tid)
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int n, int tid)
 {
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    if (!ACC && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         const int n4 = n >> 2;
         const float4* s4 = reinterpret_cast<const float4*>(src);
-        const float4* o4 = reinterpret_cast<const float4*>(old);
         float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = tid; i < n4; i += kPB) {
-            float4 v = s4[i];
-            if (ACC) {
-                const float4 o = o4[i];
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            d4[i] = v;
-        }
-        for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = ACC ? old[i] + src[i] : src[i];
+        for (int i = tid; i < n4; i += kPB) d4[i] = s4[i];
+        for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = src[i];
     } else {
-        for (int i = tid; i < n; i += kPB) dst[i] = ACC ? old[i] + src[i] : src[i];
+        for (int i = tid; i < n; i += kPB) dst[i] = ACC ? dst[i] + src[i] : src[i];
     }
 }
-
 
 }  // namespace gsr

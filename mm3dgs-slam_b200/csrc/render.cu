@@ -22,6 +22,7 @@
 //    wasted evaluation); the 9 per-splat gradient terms are reduced over the warp with a transposing
 //    butterfly (14 shuffles instead of 45) and leave as ONE fire-and-forget RED.ADD.F32 per
 //    (warp, splat, term) instead of one atomicAdd per (pixel, splat, term).
+#include "async_copy.cuh"
 #include "gsr_internal.cuh"
 #include "gsr_cull.cuh"
 
@@ -67,14 +68,18 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
     int W, int H, int gx, const uint2* __restrict__ ranges,
     const uint32_t* __restrict__ point_list, const float4* __restrict__ rec, const float* __restrict__ bg,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-    uint8_t* __restrict__ contrib, const float* __restrict__ extra, float* __restrict__ out_extra)
+    uint8_t* __restrict__ contrib, const float* __restrict__ extra, float* __restrict__ out_extra,
+    const uint32_t* __restrict__ counters, uint32_t cap)
 {
-    __shared__ float4 s_r0[kBatch];  // px, py, depth, cull r^2
-    __shared__ float4 s_r1[kBatch];  // conic xyz, opacity
-    __shared__ float4 s_r2[kBatch];  // rgb, bits
-    __shared__ float s_ex[EXTRA ? kBatch * 3 : 1];
-    __shared__ uint32_t s_mask[2][kBatch / 32][8];   // [buffer][32-entry group][warp]: entries this warp blended
+    // two stages of 256 staged records: batch k+1 is gathered by cp.async (LDGSTS, 3 x 16 B per record) while the
+    // warps blend batch k; one block barrier per batch
+    __shared__ float4 s_r0[2][kBatch];  // px, py, depth, cull r^2
+    __shared__ float4 s_r1[2][kBatch];  // conic xyz, opacity
+    __shared__ float4 s_r2[2][kBatch];  // rgb, bits
+    __shared__ float s_ex[2][EXTRA ? kBatch * 3 : 1];
+    __shared__ uint32_t s_mask[2][kBatch / 32][8];   // [stage][32-entry group][warp]: entries this warp blended
 
+    if (counters[kCntR] > cap) return;   // the instance list did not fit the caller's workspace: the host re-runs the call
     const int tile = ((int)blockIdx.x);
     const TileGeom g = tile_geom(tile, gx, W, H);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,9 +94,32 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
     bool done = !g.inside;
     bool warp_done = __all_sync(kFull, done);
 
+    // gather of one batch into stage `st`: every thread copies the record of one list entry
+    auto gather = [&](int i, int st, uint32_t id) {
+        if (i < n) {
+            const float4* r = rec + (size_t)id * 3;
+            cp_async16(&s_r0[st][threadIdx.x], r);
+            cp_async16(&s_r1[st][threadIdx.x], r + 1);
+            cp_async16(&s_r2[st][threadIdx.x], r + 2);
+            if (EXTRA) {
+                const float* e = extra + (size_t)id * 3;
+                cp_async4(&s_ex[st][3 * threadIdx.x + 0], e);
+                cp_async4(&s_ex[st][3 * threadIdx.x + 1], e + 1);
+                cp_async4(&s_ex[st][3 * threadIdx.x + 2], e + 2);
+            }
+        }
+        cp_async_commit();
+    };
+    const uint32_t* my_list = point_list + range.x + threadIdx.x;
+    gather((int)threadIdx.x, 0, (int)threadIdx.x < n ? my_list[0] : 0u);
+    uint32_t id_next = (kBatch + (int)threadIdx.x < n) ? my_list[kBatch] : 0u;   // ids run one batch ahead of the gathers
+
     int buf = 0;
     for (int base = 0;; base += kBatch) {
-        const bool all_done = __syncthreads_and(warp_done);   // also: every warp has finished the previous batch
+        cp_async_wait<0>();
+        // this thread's copies of batch `base` have landed; after the barrier everybody's have, and every warp has
+        // finished batch base-kBatch (stage buf^1 is free)
+        const bool all_done = __syncthreads_and(warp_done);
         if (base > 0) {
             // contribution byte of the previous batch's entry t: bit w set <=> warp w blended it for some pixel.
             // The backward visits exactly these (warp, entry) pairs and nothing else.
@@ -105,34 +133,27 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
             }
         }
         if (base >= n || all_done) break;
-        const int i = base + (int)threadIdx.x;
-        if (i < n) {
-            const uint32_t id = point_list[range.x + i];
-            const float4* r = rec + (size_t)id * 3;
-            s_r0[threadIdx.x] = __ldg(r);
-            s_r1[threadIdx.x] = __ldg(r + 1);
-            s_r2[threadIdx.x] = __ldg(r + 2);
-            if (EXTRA) {
-                const float* e = extra + (size_t)id * 3;
-                s_ex[3 * threadIdx.x + 0] = __ldg(e);
-                s_ex[3 * threadIdx.x + 1] = __ldg(e + 1);
-                s_ex[3 * threadIdx.x + 2] = __ldg(e + 2);
-            }
+        if (base + kBatch < n) {
+            gather(base + kBatch + (int)threadIdx.x, buf ^ 1, id_next);
+            id_next = (base + 2 * kBatch + (int)threadIdx.x < n) ? my_list[base + 2 * kBatch] : 0u;
         }
-        if (threadIdx.x < 64) s_mask[buf][threadIdx.x >> 3][threadIdx.x & 7] = 0u;
-        __syncthreads();
         const int cur = buf;
         buf ^= 1;
+        if (lane < kBatch / 32) s_mask[cur][lane][warp] = 0u;   // groups this warp does not reach stay "not blended"
+        __syncwarp();
         if (warp_done) continue;
+        const float4* r0s = s_r0[cur];
+        const float4* r1s = s_r1[cur];
+        const float4* r2s = s_r2[cur];
         const int cnt = min(kBatch, n - base);
         for (int k = 0; k < cnt; k += 32) {
             bool hit = false;
             if (k + lane < cnt) {
-                const float4 a = s_r0[k + lane];
+                const float4 a = r0s[k + lane];
                 hit = subtile_hit(g.sx0, g.sx1, g.sy0, g.sy1, a.x, a.y, a.w);
                 if (hit) {
-                    const float4 co = s_r1[k + lane];
-                    hit = subtile_hit_ellipse(g.sx0, g.sx1, g.sy0, g.sy1, a.x, a.y, co.x, co.y, co.z, s_r2[k + lane].w);
+                    const float4 co = r1s[k + lane];
+                    hit = subtile_hit_ellipse(g.sx0, g.sx1, g.sy0, g.sy1, a.x, a.y, co.x, co.y, co.z, r2s[k + lane].w);
                 }
             }
             unsigned m = __ballot_sync(kFull, hit);
@@ -141,8 +162,8 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
                 const int bit = __ffs(m) - 1;
                 const int j = k + bit;
                 m &= m - 1;
-                const float4 a = s_r0[j];
-                const float4 co = s_r1[j];
+                const float4 a = r0s[j];
+                const float4 co = r1s[j];
                 const float dx = a.x - pixx, dy = a.y - pixy;
                 const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
                 const float alpha = fminf(0.99f, co.w * expf(power));
@@ -152,15 +173,15 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
                     if (test_T < 0.0001f) {
                         done = true;
                     } else {
-                        const float4 c = s_r2[j];
+                        const float4 c = r2s[j];
                         const float w = alpha * T;
                         C0 += c.x * w;
                         C1 += c.y * w;
                         C2 += c.z * w;
                         if (EXTRA) {
-                            E0 += s_ex[3 * j + 0] * w;
-                            E1 += s_ex[3 * j + 1] * w;
-                            E2 += s_ex[3 * j + 2] * w;
+                            E0 += s_ex[cur][3 * j + 0] * w;
+                            E1 += s_ex[cur][3 * j + 1] * w;
+                            E2 += s_ex[cur][3 * j + 2] * w;
                         }
                         T = test_T;
                         last_contributor = (uint32_t)(base + j + 1);
@@ -194,14 +215,15 @@ __global__ void __launch_bounds__(256, EXTRA ? 6 : kFwdMinCtas) k_render_fwd(
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,
-                       uint8_t* contrib, const float* extra, float* out_extra, cudaStream_t s)
+                       uint8_t* contrib, const float* extra, float* out_extra, const uint32_t* counters, uint32_t cap,
+                       cudaStream_t s)
 {
     if (extra != nullptr)
         k_render_fwd<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
-                                                   out_color, contrib, extra, out_extra);
+                                                   out_color, contrib, extra, out_extra, counters, cap);
     else
         k_render_fwd<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
-                                                    out_color, contrib, nullptr, nullptr);
+                                                    out_color, contrib, nullptr, nullptr, counters, cap);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -227,12 +249,13 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : kBwdMinCtas) k_render_bwd(int
                                                     const float* __restrict__ dL_dpix_extra,
                                                     float* __restrict__ dL_dextra)
 {
-    __shared__ float4 s_r0[kBatch];
-    __shared__ float4 s_r1[kBatch];
-    __shared__ float4 s_r2[kBatch];
-    __shared__ float s_ex[EXTRA ? kBatch * 3 : 1];
-    __shared__ uint32_t s_id[kBatch];
-    __shared__ uint8_t s_cb[kBatch];     // forward's contribution byte: bit w <=> warp w blended this entry
+    // two stages: batch k+1 (the entries somebody blended) is gathered by cp.async while the warps work on batch k
+    __shared__ float4 s_r0[2][kBatch];
+    __shared__ float4 s_r1[2][kBatch];
+    __shared__ float4 s_r2[2][kBatch];
+    __shared__ float s_ex[2][EXTRA ? kBatch * 3 : 1];
+    __shared__ uint32_t s_id[2][kBatch];
+    __shared__ uint8_t s_cb[2][kBatch];     // forward's contribution byte: bit w <=> warp w blended this entry
     __shared__ uint32_t s_max;
 
     const int tile = ((int)blockIdx.x);
@@ -284,48 +307,70 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : kBwdMinCtas) k_render_bwd(int
     __syncthreads();
     const int bmax = (int)s_max;   // CTA-wide last contributor: nothing behind it matters
 
-    for (int hi = bmax; hi > 0; hi -= kBatch) {
-        // staged slot t holds list position hi-1-t (back to front)
-        const int cnt = min(kBatch, hi);
-        __syncthreads();
-        {
-            const int t = threadIdx.x;
-            uint8_t cb = 0;
-            if (t < cnt) {
-                const uint32_t p = range.x + (uint32_t)(hi - 1 - t);
-                cb = contrib[p];
-                if (cb) {   // entries nobody blended are never visited: skip their gather
-                    const uint32_t id = point_list[p];
-                    const float4* r = rec + (size_t)id * 3;
-                    s_id[t] = id;
-                    s_r0[t] = __ldg(r);
-                    s_r1[t] = __ldg(r + 1);
-                    s_r2[t] = __ldg(r + 2);
-                    if (EXTRA) {
-                        const float* e = extra + (size_t)id * 3;
-                        s_ex[3 * t + 0] = __ldg(e);
-                        s_ex[3 * t + 1] = __ldg(e + 1);
-                        s_ex[3 * t + 2] = __ldg(e + 2);
-                    }
-                }
-            }
-            s_cb[t] = cb;
+    // staged slot t of the batch that ends at list position `hi` holds position hi-1-t (back to front).  The
+    // (contribution byte, Gaussian id) pair of a slot is fetched one batch ahead of its record gather.
+    auto fetch = [&](int hi, uint8_t& cb, uint32_t& id) {
+        cb = 0;
+        id = 0;
+        const int t = threadIdx.x;
+        if (hi > 0 && t < min(kBatch, hi)) {
+            const uint32_t p = range.x + (uint32_t)(hi - 1 - t);
+            cb = contrib[p];
+            if (cb) id = point_list[p];   // entries nobody blended are never visited: skip their gather
         }
-        __syncthreads();
+    };
+    auto gather = [&](int st, uint8_t cb, uint32_t id) {
+        const int t = threadIdx.x;
+        s_cb[st][t] = cb;
+        if (cb) {
+            const float4* r = rec + (size_t)id * 3;
+            s_id[st][t] = id;
+            cp_async16(&s_r0[st][t], r);
+            cp_async16(&s_r1[st][t], r + 1);
+            cp_async16(&s_r2[st][t], r + 2);
+            if (EXTRA) {
+                const float* e = extra + (size_t)id * 3;
+                cp_async4(&s_ex[st][3 * t + 0], e);
+                cp_async4(&s_ex[st][3 * t + 1], e + 1);
+                cp_async4(&s_ex[st][3 * t + 2], e + 2);
+            }
+        }
+        cp_async_commit();
+    };
+    uint8_t cb_next;
+    uint32_t id_next;
+    fetch(bmax, cb_next, id_next);
+    gather(0, cb_next, id_next);
+    fetch(bmax - kBatch, cb_next, id_next);
+
+    int buf = 0;
+    for (int hi = bmax; hi > 0; hi -= kBatch) {
+        const int cnt = min(kBatch, hi);
+        cp_async_wait<0>();
+        __syncthreads();   // batch `hi` has landed for everybody; every warp is done with the other stage
+        if (hi - kBatch > 0) {
+            gather(buf ^ 1, cb_next, id_next);
+            fetch(hi - 2 * kBatch, cb_next, id_next);
+        }
+        const int cur = buf;
+        buf ^= 1;
+        const float4* r0s = s_r0[cur];
+        const float4* r1s = s_r1[cur];
+        const float4* r2s = s_r2[cur];
         // first slot this warp cares about: position < wmax  <=>  t > hi-1-wmax
         int t0 = hi - (int)wmax;
         if (t0 < 0) t0 = 0;
         for (int k = (t0 & ~31); k < cnt; k += 32) {
             const int tt = k + lane;
-            const bool hit = (tt < cnt) && ((s_cb[tt] >> warp) & 1u);   // this warp blended it in the forward
+            const bool hit = (tt < cnt) && ((s_cb[cur][tt] >> warp) & 1u);   // this warp blended it in the forward
             unsigned m = __ballot_sync(kFull, hit);
             while (m) {
                 const int b = __ffs(m) - 1;
                 const int j = k + b;
                 m &= m - 1;
                 const uint32_t pos = (uint32_t)(hi - 1 - j);   // 0-based list position
-                const float4 a = s_r0[j];
-                const float4 co = s_r1[j];
+                const float4 a = r0s[j];
+                const float4 co = r1s[j];
                 const float dx = a.x - pixx, dy = a.y - pixy;
                 const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
                 const float G = expf(power);
@@ -334,7 +379,7 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : kBwdMinCtas) k_render_bwd(int
                 float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
                 float v9 = 0.f, v10 = 0.f, v11 = 0.f;
                 if (live) {
-                    const float4 c = s_r2[j];
+                    const float4 c = r2s[j];
                     const float inv_1ma = __frcp_rn(1.f - alpha);
                     T = T * inv_1ma;
                     const float dchannel_dcolor = alpha * T;
@@ -352,7 +397,7 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : kBwdMinCtas) k_render_bwd(int
                     v7 = dchannel_dcolor * dLp1;
                     v8 = dchannel_dcolor * dLp2;
                     if (EXTRA) {
-                        const float e0c = s_ex[3 * j + 0], e1c = s_ex[3 * j + 1], e2c = s_ex[3 * j + 2];
+                        const float e0c = s_ex[cur][3 * j + 0], e1c = s_ex[cur][3 * j + 1], e2c = s_ex[cur][3 * j + 2];
                         acc3 = last_alpha * lc3 + (1.f - last_alpha) * acc3;
                         lc3 = e0c;
                         dL_dalpha += (e0c - acc3) * dLe0;
@@ -402,11 +447,11 @@ __global__ void __launch_bounds__(256, EXTRA ? 4 : kBwdMinCtas) k_render_bwd(int
                         h0 += __shfl_xor_sync(kFull, h0, 4);
                         h0 += __shfl_xor_sync(kFull, h0, 2);
                         h0 += __shfl_xor_sync(kFull, h0, 1);   // lanes with (b4, b3): term 8 + 2*b4 + b3
-                        if (red_base != nullptr && lane != 1) atomicAdd(red_base + (size_t)s_id[j] * red_stride, e0);
-                        if (red2_base != nullptr) atomicAdd(red2_base + (size_t)s_id[j] * 3, h0);
+                        if (red_base != nullptr && lane != 1) atomicAdd(red_base + (size_t)s_id[cur][j] * red_stride, e0);
+                        if (red2_base != nullptr) atomicAdd(red2_base + (size_t)s_id[cur][j] * 3, h0);
                     } else {
                         v8 = warp_sum(v8);
-                        if (red_base != nullptr) atomicAdd(red_base + (size_t)s_id[j] * red_stride, lane == 1 ? v8 : e0);
+                        if (red_base != nullptr) atomicAdd(red_base + (size_t)s_id[cur][j] * red_stride, lane == 1 ? v8 : e0);
                     }
                 }
             }

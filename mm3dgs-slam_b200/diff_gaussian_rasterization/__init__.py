@@ -94,7 +94,7 @@ def _load():
                                  ctypes.POINTER(_Grads)]
     lib.gsr_mark_visible.restype = ctypes.c_int
     lib.gsr_mark_visible.argtypes = [vp, i32, vp, vp, vp, vp]
-    if lib.gsr_abi_version() != 3:
+    if lib.gsr_abi_version() != 4:
         raise ImportError("libgsrast_b200.so ABI version mismatch")
     return lib
 
@@ -125,7 +125,15 @@ def _prep(t, device):
 
 
 def _snapshot(args, path):
-    torch.save(tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args), path)
+    """Argument dump on failure (debug mode), like the reference's: tensors and plain scalars only — handles that wrap
+    ctypes structs / streams / events (PreparedFrame) cannot be pickled and would hide the original error."""
+    def keep(a):
+        if isinstance(a, torch.Tensor):
+            return a.detach().cpu().clone()
+        if isinstance(a, tuple) and hasattr(a, "_fields"):     # raster settings
+            return type(a)(*[keep(x) for x in a])
+        return a if isinstance(a, (int, float, bool, str, type(None))) else None
+    torch.save(tuple(keep(a) for a in args), path)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -152,19 +160,79 @@ class _GeomLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "rects", "depth_keys", "sorted_ids", "counters", "total")]
 
 
-_pinned_pool = {}
+class _SlotPool:
+    """Pinned int32 slots for the device->host hand-off of the instance count R (cudaHostAlloc is far too slow to
+    call per frame).  A slot is handed out once and comes back when its consumer has read it, so any number of
+    frames can be in flight without two of them sharing a slot; the pool grows in blocks of 64."""
+
+    def __init__(self):
+        self.free = []
+        self.blocks = []
+
+    def get(self):
+        if not self.free:
+            blk = torch.empty(64, dtype=torch.int32).pin_memory()
+            self.blocks.append(blk)
+            self.free.extend(blk[i: i + 1] for i in range(64))
+        return self.free.pop()
+
+    def put(self, slot):
+        self.free.append(slot)
 
 
-def _pinned_slot(dev):
-    """Small ring of pinned int32 slots per device (cudaHostAlloc is far too slow to call per frame)."""
-    ring = _pinned_pool.setdefault(dev.index, {"buf": torch.empty(256, dtype=torch.int32).pin_memory(), "i": 0})
-    ring["i"] = (ring["i"] + 1) % 256
-    return ring["buf"][ring["i"]: ring["i"] + 1]
+_slots = _SlotPool()
+# last seen instance counts per (device, P, W, H): capacity estimate of the next forward's instance list
+_r_seen = {}
+
+
+def _validate(means3D, extra_colors):
+    """Argument checks shared by the autograd forward and prepare_forward (same messages as the reference where it
+    has them: DGR/rasterize_points.cu:57-59)."""
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("gsrast_b200: tensors must live on a CUDA device (there is no CPU path)")
+    if isinstance(extra_colors, str):
+        if extra_colors != DEPTH_SILHOUETTE:
+            raise ValueError("extra_colors must be a [P,3] tensor or diff_gaussian_rasterization.DEPTH_SILHOUETTE")
+    elif extra_colors is not None and extra_colors.numel() != 0:
+        if extra_colors.dim() != 2 or tuple(extra_colors.shape) != (means3D.shape[0], 3):
+            raise RuntimeError("extra_colors must have dimensions (num_points, 3)")
+
+
+def _extra_key(extra):
+    """Identity of the extra-colour argument a frame was prepared / rendered with."""
+    if isinstance(extra, str):
+        return extra
+    if extra is None or extra.numel() == 0:
+        return None
+    return extra.data_ptr()
 
 
 class PreparedFrame:
     """Phase 1 of a forward (projection + depth sort) already enqueued; see prepare_forward()."""
-    __slots__ = ("tensors", "rs", "radii", "geom", "img", "r_host", "event", "stream", "g", "c")
+    __slots__ = ("tensors", "rs", "radii", "geom", "img", "r_host", "event", "stream", "g", "c", "key")
+
+    def release(self):
+        if getattr(self, "r_host", None) is not None:
+            _slots.put(self.r_host)
+            self.r_host = None
+
+
+def _input_key(t, extra):
+    """Device pointers of everything phase 1 read: a prepared handle is only valid for exactly these inputs."""
+    return tuple(None if (x is None or x.numel() == 0) else x.data_ptr() for x in t) + (_extra_key(extra),)
+
+
+def _enqueue_r_copy(geom, P, W, H, stream):
+    """Asynchronous copy of the device-side instance count into a pinned slot + an event after it."""
+    lay = _GeomLayout()
+    _lib.gsr_geom_layout_of(ctypes.c_int32(P), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(lay))
+    slot = _slots.get()
+    slot.copy_(geom[lay.counters: lay.counters + 4].view(torch.int32), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return slot, ev
 
 
 def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precomp=None, scales=None, rotations=None,
@@ -174,8 +242,12 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
     SAME tensors and settings.  Issuing phase 1 of several frames before the first forward() means every
     frame's R is already on the host when its forward() needs it — the host never stalls on the hand-off."""
     rs = raster_settings
-    if not means3D.is_cuda:
-        raise RuntimeError("gsrast_b200: tensors must live on a CUDA device (there is no CPU path)")
+    _validate(means3D, extra_colors)
+    if (shs is None) == (colors_precomp is None):
+        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+    if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+            (scales is not None or rotations is not None) and cov3D_precomp is not None):
+        raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
     dev = means3D.device
     e = torch.Tensor([])
     with torch.cuda.device(dev):
@@ -187,10 +259,12 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
         H, W = int(rs.image_height), int(rs.image_width)
         pf = PreparedFrame()
         pf.tensors, pf.rs = tuple(t) + (extra,), rs
+        pf.key = _input_key(t, extra)
         pf.stream = torch.cuda.current_stream(dev)
         pf.radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        pf.r_host = None
         if P == 0:
-            pf.geom = pf.img = pf.r_host = pf.event = None
+            pf.geom = pf.img = pf.event = None
             return pf
         u8 = dict(dtype=torch.uint8, device=dev)
         pf.geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
@@ -200,57 +274,85 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
         _check(_lib.gsr_forward_preprocess(pf.stream.cuda_stream, ctypes.byref(pf.g), ctypes.byref(pf.c),
                                            pf.radii.data_ptr(), pf.geom.data_ptr(), pf.geom.numel(), pf.img.data_ptr(),
                                            pf.img.numel(), None))
-        lay = _GeomLayout()
-        _lib.gsr_geom_layout_of(ctypes.c_int32(P), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(lay))
-        pf.r_host = _pinned_slot(dev)
-        pf.r_host.copy_(pf.geom[lay.counters: lay.counters + 4].view(torch.int32), non_blocking=True)
-        pf.event = torch.cuda.Event()
-        pf.event.record(pf.stream)
+        pf.r_host, pf.event = _enqueue_r_copy(pf.geom, P, W, H, pf.stream)
     return pf
 
 
 def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
                     extra=None, prepared=None):
     """Returns (R, color, radii, geom, binning, img); with `extra` ([P,3] colours) the 7th element is the
-    extra [3,H,W] image blended in the same pass."""
+    extra [3,H,W] image blended in the same pass.  R is the capacity the binning workspace was carved with (what
+    gsr_backward needs); it is >= the true instance count.
+
+    The host never waits for the GPU to drain: phase 2 is enqueued against a capacity ESTIMATE of the instance list
+    (the largest count seen for this problem size, plus a margin) right behind phase 1, and only then does the host
+    look at the true count — by which time the projection kernel that produces it has long finished while the rest of
+    the forward is still queued.  If the estimate was too small (the kernels then leave the outputs untouched) phase 2
+    is simply enqueued again with the exact size."""
     dev = means3D.device
     P = means3D.shape[0]
     H, W = int(rs.image_height), int(rs.image_width)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    cur = torch.cuda.current_stream(dev)
+    stream = cur.cuda_stream
     u8 = dict(dtype=torch.uint8, device=dev)
     color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-    radii = torch.empty((P,), dtype=torch.int32, device=dev)
     has_extra = isinstance(extra, str) or (extra is not None and extra.numel() != 0)
     extra_img = torch.empty((3, H, W), dtype=torch.float32, device=dev) if has_extra else None
     if P == 0:
         color.zero_()
         e = torch.empty(0, **u8)
+        radii = torch.empty((0,), dtype=torch.int32, device=dev)
         return (0, color, radii, e, e, e) + ((torch.zeros_like(color),) if extra is not None else ())
+    R = None
     if prepared is not None:
-        if prepared.tensors[0].data_ptr() != means3D.data_ptr() or prepared.radii.shape[0] != P or prepared.rs is not rs:
+        key = _input_key((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, view, proj, campos,
+                          bg), extra)
+        if prepared.key != key or prepared.radii.shape[0] != P or prepared.rs is not rs:
             raise RuntimeError("gsrast_b200: `prepared` was made for different inputs / settings")
         radii, geom, img, g, c = prepared.radii, prepared.geom, prepared.img, prepared.g, prepared.c
-        cur = torch.cuda.current_stream(dev)
         if cur != prepared.stream:
             cur.wait_stream(prepared.stream)
-        prepared.event.synchronize()
-        R = int(prepared.r_host.item())
-        if R < 0:
-            raise RuntimeError("gsrast_b200: more than 2^31-1 tile instances")
+        slot, event = prepared.r_host, prepared.event
+        prepared.r_host = None                     # the slot goes back to the pool below
+        if event.query():                          # usually true: phase 1 was enqueued frames ago
+            R = int(slot.item())
     else:
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
         img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
         g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos,
                         bg, extra if has_extra else None)
-        R = ctypes.c_int32(0)
         _check(_lib.gsr_forward_preprocess(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), geom.data_ptr(),
-                                           geom.numel(), img.data_ptr(), img.numel(), ctypes.byref(R)))
-        R = int(R.value)
-    binning = torch.empty(_lib.gsr_binning_ws_bytes(R), **u8)
-    _check(_lib.gsr_forward_render(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, geom.data_ptr(),
-                                   binning.data_ptr(), binning.numel(), img.data_ptr(), color.data_ptr(),
-                                   _ptr(extra_img)))
-    return (R, color, radii, geom, binning, img) + ((extra_img,) if has_extra else ())
+                                           geom.numel(), img.data_ptr(), img.numel(), None))
+        slot, event = _enqueue_r_copy(geom, P, W, H, cur)
+    ckey = (dev.index, P, W, H)
+    seen = _r_seen.get(ckey)
+
+    def render(cap):
+        binning = torch.empty(_lib.gsr_binning_ws_bytes(cap), **u8)
+        _check(_lib.gsr_forward_render(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), cap, geom.data_ptr(),
+                                       binning.data_ptr(), binning.numel(), img.data_ptr(), color.data_ptr(),
+                                       _ptr(extra_img)))
+        return binning
+
+    if R is None and seen is not None:
+        cap = seen + (seen >> 2) + 65536           # estimate: phase 2 goes out before the host has seen R
+        binning = render(cap)
+        event.synchronize()
+        R = int(slot.item())
+    else:
+        if R is None:                              # first call for this problem size: wait for the count
+            event.synchronize()
+            R = int(slot.item())
+        cap, binning = -1, None
+    _slots.put(slot)
+    if R < 0:
+        raise RuntimeError("gsrast_b200: more than 2^31-1 tile instances")
+    _r_seen[ckey] = R if seen is None else max(R, seen - (seen >> 6))   # running maximum with a slow decay
+    if R > cap:
+        cap = R
+        binning = render(cap)
+    return (cap, color, radii, geom, binning, img) + ((extra_img,) if has_extra else ())
 
 
 def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view,
@@ -338,23 +440,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                         or t.numel() != src[k].numel()):
                     raise ValueError(f"grad_targets['{k}'] must be a contiguous fp32 CUDA tensor shaped like the input")
         ctx.grad_targets = grad_targets if grad_targets else None
-        if means3D.dim() != 2 or means3D.shape[1] != 3:
-            raise RuntimeError("means3D must have dimensions (num_points, 3)")
-        if not means3D.is_cuda:
-            raise RuntimeError("gsrast_b200: tensors must live on a CUDA device (there is no CPU path)")
+        _validate(means3D, extra_colors)
         dev = means3D.device
         with torch.cuda.device(dev):
             t = [_prep(x, dev) for x in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                          viewmatrix, projmatrix, campos, rs.bg)]
             means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_ = t
-            if isinstance(extra_colors, str):
-                if extra_colors != DEPTH_SILHOUETTE:
-                    raise ValueError("extra_colors must be a [P,3] tensor or diff_gaussian_rasterization.DEPTH_SILHOUETTE")
-                extra_ = extra_colors
-            else:
-                extra_ = _prep(extra_colors, dev)
-                if extra_ is not None and (extra_.dim() != 2 or extra_.shape != (means3D.shape[0], 3)):
-                    raise RuntimeError("extra_colors must have dimensions (num_points, 3)")
+            extra_ = extra_colors if isinstance(extra_colors, str) else _prep(extra_colors, dev)
             args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_, prepared)
             if rs.debug:
                 try:

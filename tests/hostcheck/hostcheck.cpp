@@ -3,6 +3,7 @@
 // Test infrastructure: compiled by the test with g++, never linked into the library.
 #include "gsr_cull.cuh"
 #include "gsr_math.cuh"
+#include "gsr_bwd_math.cuh"
 #include <string.h>
 
 using namespace gsr;
@@ -45,16 +46,19 @@ void hc_forward(int P, int deg, int M, const float* means, const float* scales, 
     }
 }
 
-// Covariance path of k_preprocess_bwd: dL/dconic -> dL/dcov3D, dL/dmean (through J and the view transform),
-// dL/dscale, dL/d(raw quaternion).  Only Gaussians with radii > 0 are touched.
+// Covariance path of k_preprocess_bwd (csrc/gsr_bwd_math.cuh): dL/dconic -> dL/dmean (through J and the view
+// transform), dL/dscale, dL/d(raw quaternion) on the (scale, rotation) path, and dL/dcov3D + dL/dmean on the
+// precomputed-covariance path (fed with the covariance the forward builds from the same scale / rotation, so both
+// paths must agree on dL/dmean).  The conic is the forward's, as in the kernel.  Only Gaussians with radii > 0 are touched.
 void hc_cov_backward(int P, const int* radii, const float* means, const float* scales, const float* rots, float mod,
-                     const float* view, int W, int H, float tanfovx, float tanfovy, const float* dconic, float* dcov,
-                     float* dmean, float* dscale, float* drot)
+                     const float* view, const float* proj, int W, int H, float tanfovx, float tanfovy, const float* dconic,
+                     float* dcov, float* dmean, float* dscale, float* drot, float* dmean_precomp)
 {
     const float focal_x = W / (2.0f * tanfovx), focal_y = H / (2.0f * tanfovy);
+    const int gx = (W + GSR_TILE - 1) / GSR_TILE, gy = (H + GSR_TILE - 1) / GSR_TILE;
     for (int i = 0; i < P; i++) {
         for (int k = 0; k < 6; k++) dcov[6 * i + k] = 0.f;
-        for (int k = 0; k < 3; k++) dmean[3 * i + k] = dscale[3 * i + k] = 0.f;
+        for (int k = 0; k < 3; k++) dmean[3 * i + k] = dscale[3 * i + k] = dmean_precomp[3 * i + k] = 0.f;
         for (int k = 0; k < 4; k++) drot[4 * i + k] = 0.f;
         if (radii[i] <= 0) continue;
         const V3 p = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
@@ -62,15 +66,33 @@ void hc_cov_backward(int P, const int* radii, const float* means, const float* s
         const V4 q = {rots[4 * i], rots[4 * i + 1], rots[4 * i + 2], rots[4 * i + 3]};
         float cov6[6];
         cov3d_from_scale_rot(sc, mod, q, cov6);
-        const Cov2DGrad g = cov2d_backward(p, cov6, focal_x, focal_y, tanfovx, tanfovy, view, dconic[3 * i],
-                                           dconic[3 * i + 1], dconic[3 * i + 2]);
-        for (int k = 0; k < 6; k++) dcov[6 * i + k] = g.dcov[k];
-        dmean[3 * i] = g.dmean.x; dmean[3 * i + 1] = g.dmean.y; dmean[3 * i + 2] = g.dmean.z;
-        V3 ds;
+        const PreOut o = preprocess_one(p, cov6, view, proj, W, H, tanfovx, tanfovy, focal_x, focal_y, gx, gy);
+        const ViewFrame f = view_frame(p, view, focal_x, focal_y, tanfovx, tanfovy);
+        const Sym2 Hq = cov2d_grad_from_conic(o.cx, o.cy, o.cz, dconic[3 * i], dconic[3 * i + 1], dconic[3 * i + 2]);
+        const V3 s_eff = {mod * sc.x, mod * sc.y, mod * sc.z};
+        V3 ds, dM0, dM1;
         V4 dq;
-        cov3d_backward(sc, mod, q, g.dcov, ds, dq);
+        cov_chain_scale_rot(f, Hq, s_eff, q, ds, dq, dM0, dM1);
+        V3 dm = view_t_mul(f, view_chain(f, dM0, dM1, focal_x, focal_y));
+        dmean[3 * i] = dm.x; dmean[3 * i + 1] = dm.y; dmean[3 * i + 2] = dm.z;
         dscale[3 * i] = ds.x; dscale[3 * i + 1] = ds.y; dscale[3 * i + 2] = ds.z;
         drot[4 * i] = dq.x; drot[4 * i + 1] = dq.y; drot[4 * i + 2] = dq.z; drot[4 * i + 3] = dq.w;
+        cov_chain_precomp(f, Hq, cov6, dcov + 6 * i, dM0, dM1);
+        dm = view_t_mul(f, view_chain(f, dM0, dM1, focal_x, focal_y));
+        dmean_precomp[3 * i] = dm.x; dmean_precomp[3 * i + 1] = dm.y; dmean_precomp[3 * i + 2] = dm.z;
+    }
+}
+
+// Screen-position path: dL/dmean2D (NDC units) -> dL/dmean.
+void hc_ndc_backward(int P, const int* radii, const float* means, const float* proj, const float* dmean2d, float* dmean)
+{
+    for (int i = 0; i < P; i++) {
+        for (int k = 0; k < 3; k++) dmean[3 * i + k] = 0.f;
+        if (radii[i] <= 0) continue;
+        const V3 p = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
+        V3 dh;
+        const V3 dm = ndc_chain(p, proj, dmean2d[2 * i], dmean2d[2 * i + 1], dh);
+        dmean[3 * i] = dm.x; dmean[3 * i + 1] = dm.y; dmean[3 * i + 2] = dm.z;
     }
 }
 
@@ -83,12 +105,12 @@ void hc_sh_backward(int P, int deg, int M, const int* radii, const int* clamp_bi
         for (int k = 0; k < 3; k++) dmean[3 * i + k] = 0.f;
         if (radii[i] <= 0) continue;
         const V3 d0 = {means[3 * i] - campos[0], means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2]};
-        const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
-        const V3 dir = {d0.x / len, d0.y / len, d0.z / len};
+        const float inv_len = GSR_RSQRT(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
+        const V3 dir = {d0.x * inv_len, d0.y * inv_len, d0.z * inv_len};
         float dRGB[3];
         for (int ch = 0; ch < 3; ch++) dRGB[ch] = ((clamp_bits[i] >> ch) & 1) ? 0.f : dcolors[3 * i + ch];
-        const V3 ddir = sh_backward(deg, shs + (size_t)i * M * 3, dir, dRGB, dsh + (size_t)i * M * 3);
-        const V3 dm = dnormvdv(d0, ddir);
+        const V3 ddir = sh_grad(deg, shs + (size_t)i * M * 3, dir, dRGB, dsh + (size_t)i * M * 3);
+        const V3 dm = unit_vector_grad(dir, inv_len, ddir);
         dmean[3 * i] = dm.x; dmean[3 * i + 1] = dm.y; dmean[3 * i + 2] = dm.z;
     }
 }

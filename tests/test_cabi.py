@@ -25,7 +25,7 @@ def test_header_symbols_exported(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/*.h but not exported"
     lib.gsr_abi_version.restype = ctypes.c_int
-    assert lib.gsr_abi_version() == 3
+    assert lib.gsr_abi_version() == 4
 
 
 def test_headers_are_plain_c(tmp_path):
@@ -35,7 +35,7 @@ def test_headers_are_plain_c(tmp_path):
     src = tmp_path / "hdr_check.c"
     src.write_text('#include "gsrast_b200.h"\n#include "gsloss_b200.h"\n'
                    "int main(void) { gsr_loss_config c; gsr_gaussians g; gsr_camera k; gsr_grads d;\n"
-                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 3 ? 0 : 1; }\n")
+                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 4 ? 0 : 1; }\n")
     inc = os.path.join(ROOT, "include")
     if shutil.which("gcc"):
         subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
@@ -58,7 +58,7 @@ def test_c_client_links_and_runs(built_lib, tmp_path):
                     os.path.join(ROOT, "tests", "c_client.c"), "-o", exe, "-L", libdir, "-lgsrast_b200",
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    assert out.startswith("abi 3 ")
+    assert out.startswith("abi 4 ")
 
 
 def test_workspace_layouts_are_sane(built_lib):

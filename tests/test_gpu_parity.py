@@ -114,13 +114,14 @@ def test_intermediate_state_bit_exact(dgr, ref, P, W, H, deg, seed):
     mb, rb = ws_decode.decode_binning(binning, R, mg, mi), ref.decode_binning(f["binning"], R)
     assert torch.equal(mb["point_list"], rb["point_list"])
     assert torch.equal(mb["keys"], rb["keys"])
-    # depth order of the Gaussians themselves: ascending (depth bits, index), culled last
-    sid = mg["sorted_ids"]
+    # depth order of the visible Gaussians themselves: ascending (depth bits, index); culled ones are dropped
+    nvis = int(vis.sum())
+    sid = mg["sorted_ids"][:nvis]
     k = mg["depth_keys"][sid]
     assert bool((k[1:] >= k[:-1]).all())
     tie = k[1:] == k[:-1]
     assert bool((sid[1:][tie] > sid[:-1][tie]).all())
-    assert torch.equal(torch.sort(sid).values, torch.arange(P))
+    assert torch.equal(torch.sort(sid).values, torch.nonzero(vis).reshape(-1))
     assert torch.equal(mi["n_contrib"], ri["n_contrib"])
     assert rel_err(mi["final_T"], ri["final_T"]) < 1e-6
     assert rel_err(color, f["color"]) < TOL

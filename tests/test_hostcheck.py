@@ -35,6 +35,13 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
 
 
+def rms_rel(a, b):
+    """Per-element differences against the RMS magnitude of the reference tensor (a wrong class of small-magnitude
+    entries shows up here even when the global-max norm hides it)."""
+    a, b = a.double(), b.double()
+    return float(torch.sqrt(((a - b) ** 2).mean()) / (torch.sqrt((b ** 2).mean()) + 1e-30))
+
+
 def _scene(P, W, H, deg, seed, cam_index):
     gs, cam, _, _ = S.make_scene(P, W, H, seed, deg)
     if cam_index is not None:
@@ -88,13 +95,23 @@ def test_backward_math_matches_oracle(hc, P, W, H, deg, seed, cam_index):
     want = O.preprocess_backward(gs["means3D"], cam.viewmatrix, cam.projmatrix, cam.campos, W, H, cam.tanfovx, cam.tanfovy,
                                  pre, dict(dL_dconic=dconic, dL_dmean2D=zero2, dL_dcolors=zero3), **kw)
     dcov, dmean, dscale, drot = torch.zeros(P, 6), torch.zeros(P, 3), torch.zeros(P, 3), torch.zeros(P, 4)
+    dmean_pre = torch.zeros(P, 3)
+    proj = cam.projmatrix.reshape(16).contiguous()
     hc.hc_cov_backward(P, _p(radii), _p(gs["means3D"]), _p(gs["scales"]), _p(gs["rotations"]), ctypes.c_float(1.0), _p(view),
-                       W, H, ctypes.c_float(cam.tanfovx), ctypes.c_float(cam.tanfovy), _p(dconic), _p(dcov), _p(dmean),
-                       _p(dscale), _p(drot))
-    assert rel(dcov, want["dL_dcov3D"]) < 1e-4
-    assert rel(dmean, want["dL_dmeans3D"]) < 1e-4
-    assert rel(dscale, want["dL_dscales"]) < 1e-4
-    assert rel(drot, want["dL_drotations"]) < 1e-4
+                       _p(proj), W, H, ctypes.c_float(cam.tanfovx), ctypes.c_float(cam.tanfovy), _p(dconic), _p(dcov),
+                       _p(dmean), _p(dscale), _p(drot), _p(dmean_pre))
+    for got, key in ((dcov, "dL_dcov3D"), (dmean, "dL_dmeans3D"), (dmean_pre, "dL_dmeans3D"), (dscale, "dL_dscales"),
+                     (drot, "dL_drotations")):
+        assert rel(got, want[key]) < 1e-4, key
+        assert rms_rel(got, want[key]) < 1e-4, key
+
+    # screen-position path: dL/dmean2D -> dL/dmean
+    dm2 = torch.randn(P, 2, generator=g)
+    want = O.preprocess_backward(gs["means3D"], cam.viewmatrix, cam.projmatrix, cam.campos, W, H, cam.tanfovx, cam.tanfovy,
+                                 pre, dict(dL_dconic=zero3, dL_dmean2D=dm2, dL_dcolors=zero3), **kw)
+    dmean = torch.zeros(P, 3)
+    hc.hc_ndc_backward(P, _p(radii), _p(gs["means3D"]), _p(proj), _p(dm2.contiguous()), _p(dmean))
+    assert rel(dmean, want["dL_dmeans3D"]) < 1e-5 and rms_rel(dmean, want["dL_dmeans3D"]) < 1e-5
 
     # SH path: clamp-masked dL/dRGB -> dL/dsh and the view-direction part of dL/dmean
     dcol = torch.randn(P, 3, generator=g)
