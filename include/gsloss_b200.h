@@ -37,7 +37,10 @@ enum gsr_depth_loss {
     GSR_DEPTH_L1_MEAN = 1,     /* mean |y - x| over the mask                              mapper.py:853 */
     GSR_DEPTH_L1_SUM = 2,      /* sum  |y - x| over the mask                              tracker.py:121 */
     GSR_DEPTH_PEARSON = 3,     /* 1 - corr(x, y) over the mask                            loss_utils.py:60 */
-    GSR_DEPTH_PEARSON_INV = 4  /* min(1 - corr(-y, x), 1 - corr(1/(y+200), x))            loss_utils.py:54-58 */
+    GSR_DEPTH_PEARSON_INV = 4, /* min(1 - corr(-y, x), 1 - corr(1/(y+200), x))            loss_utils.py:54-58 */
+    GSR_DEPTH_PEARSON_COLS = 5 /* mean over the W image columns c of 1 - corr(x[:, c], y[:, c]): what the reference's
+                                * UNMASKED call computes, because torchmetrics reads a 2-D [H,W] input as H samples of W
+                                * outputs (loss_utils.py:52-53,60 with mask=None, mapper.py:862-868).  depth_mask must be 0 */
 };
 
 /* Mask terms, AND-ed; a zero flag set means "all pixels".  The masks carry no gradient (the reference

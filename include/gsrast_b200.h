@@ -177,7 +177,7 @@ typedef struct gsr_geom_layout {
     size_t rec;        /* float4[3P]: (px,py,depth,cull_r2) (conic.x,conic.y,conic.z,opacity) (r,g,b,clamp bits) */
     size_t rects;      /* ushort4[P]: tile rectangle {x0,y0,x1,y1}, empty for culled Gaussians */
     size_t depth_keys; /* uint32[P]: float bits of the view depth, 0xFFFFFFFF for culled Gaussians */
-    size_t sorted_ids; /* uint32[P]: the VISIBLE Gaussians' ids in (depth, index) order (counters[2] entries) */
+    size_t sorted_ids; /* uint2[P]: {depth key, id} of the VISIBLE Gaussians in (depth, index) order (counters[2] entries) */
     size_t counters;   /* uint32[>=3]: [0] = R, the number of tile instances; [2] = number of visible Gaussians
                         * (valid after gsr_forward_preprocess) */
     size_t total;

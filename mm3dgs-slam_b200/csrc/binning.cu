@@ -31,8 +31,6 @@
 namespace gsr {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kDigitBits = 11;
-constexpr int kBins = 1 << kDigitBits;       // 2048
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 8;                // keys per thread (4 measured slower)
@@ -97,40 +95,47 @@ __device__ __forceinline__ void block_exclusive_scan(uint32_t* s_data, uint32_t*
 // ================================================================================================
 // 1. Depth sort (visible Gaussians only)
 // ================================================================================================
-// Three single-kernel LSD passes (11 / 11 / 10 bits) in the "onesweep" form: the three global digit histograms
-// are accumulated by k_preprocess_fwd while the key is still in a register, so a pass only has to rank its 4096-key
-// block locally (per-warp 16-bit counters, MATCH.ANY) and find how many keys with the same digit precede the block —
-// by decoupled look-back over the blocks' published per-digit counts instead of a count kernel + a column-scan
-// kernel.  Blocks take their index from a ticket counter, so every block a look-back waits on is already running.
-// Pass 0 drops the culled Gaussians (key 0xFFFFFFFF): passes 1 and 2 and the tile partition only see the visible ones.
+// Four single-kernel LSD passes over 8-bit digits in the "onesweep" form.  The four global digit histograms are
+// accumulated by k_preprocess_fwd while the key is still in a register, so a pass only has to
+//   (1) rank its 4096-key block locally (MATCH.ANY + per-warp 16-bit counters, one dependent sweep),
+//   (2) learn how many keys with the same digit precede the block: decoupled look-back over the blocks' published
+//       per-digit counts, one digit per thread, four predecessors in flight per step.  Blocks take their index from
+//       a ticket counter, so every block a look-back waits on is already running;
+//   (3) reorder the block in shared memory by digit and write it out as runs (about 16 pairs = 128 B per digit and
+//       block), so the scatter costs a few store wavefronts per warp instead of one per key.
+// 8-bit digits rather than the 11/11/10 split of a count / scan / scatter sort: with 256 digits a 4096-key block
+// holds runs, the per-warp counters are 8 KB instead of 64 KB, and a look-back step is one 1 KB row.
+// Pass 0 drops the culled Gaussians (key 0xFFFFFFFF): later passes and the tile partition only see the visible ones.
+// Keys travel with their Gaussian id as one 8-byte pair; pass 0 reads the bare depth keys (the id is the index).
 //
-// status[block][bin]: bits 31..29 tag, bits 28..0 count.  tag 2p+1 = block's own count for pass p, tag 2p+2 = inclusive
-// prefix over blocks 0..block; anything else = not published yet for this pass (the array is zeroed once per frame and
-// reused by the three passes).
-constexpr uint32_t kStatMask = 0x1fffffffu;
+// status[block][digit]: bits 31..28 tag, bits 27..0 count.  For pass p, tag 2p+1 = the block's own count, tag 2p+2 =
+// inclusive prefix over blocks 0..block; anything else = not published yet for this pass (the array is zeroed once per
+// frame and reused by the four passes).
+constexpr uint32_t kStatMask = 0x0fffffffu;
+constexpr int kRadixBits = 8;
+constexpr int kRBins = 1 << kRadixBits;
 
 __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 template <int PASS>
 __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* __restrict__ keys_in,
-                                                               const uint32_t* __restrict__ vals_in, int n_in,
+                                                               const uint2* __restrict__ pairs_in, int n_in,
                                                                const uint32_t* __restrict__ ghist, uint32_t* status,
-                                                               uint32_t* counters, uint32_t* __restrict__ keys_out,
-                                                               uint32_t* __restrict__ vals_out)
+                                                               uint32_t* counters, uint2* __restrict__ pairs_out)
 {
-    extern __shared__ uint32_t s_dyn[];
-    uint32_t* s_start = s_dyn;                                                    // [kBins] destination of this block's first key per bin
-    uint16_t (*s_cnt)[kBins] = reinterpret_cast<uint16_t (*)[kBins]>(s_dyn + kBins);  // [kSortWarps][kBins] per-warp counters
-    __shared__ uint32_t s_scan[kSortWarps];
-    __shared__ uint32_t s_block;
-    constexpr int shift = 11 * PASS;
-    constexpr uint32_t mask = PASS == 2 ? 1023u : 2047u;
-    constexpr uint32_t tag_agg = (uint32_t)(2 * PASS + 1) << 29, tag_incl = (uint32_t)(2 * PASS + 2) << 29;
+    __shared__ uint2 s_pairs[kSortChunk];                 // the block, reordered by digit (32 KB)
+    __shared__ uint16_t s_cnt[kSortWarps][kRBins];        // per-warp digit counters -> exclusive prefix over the warps
+    __shared__ uint32_t s_lstart[kRBins];                 // first local slot of each digit
+    __shared__ uint32_t s_gdst[kRBins];                   // global destination of local slot 0 of each digit's run
+    __shared__ uint32_t s_warp[kRBins / 32];
+    __shared__ uint32_t s_block, s_total;
+    constexpr int shift = kRadixBits * PASS;
+    constexpr uint32_t mask = kRBins - 1;
+    constexpr uint32_t tag_agg = (uint32_t)(2 * PASS + 1) << 28, tag_incl = (uint32_t)(2 * PASS + 2) << 28;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) s_block = atomicAdd(&counters[kCntTicket + PASS], 1u);
-    for (int b = tid; b < kBins; b += kSortThreads) s_start[b] = ghist[PASS * kBins + b];
     __syncthreads();
     const int block = (int)s_block;
     const int n = PASS == 0 ? n_in : (int)counters[kCntVisible];
@@ -142,17 +147,35 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         const int i = wbase + j * 32 + lane;
-        key[j] = (i < n) ? keys_in[i] : 0xffffffffu;
-        val[j] = (PASS == 0 || i >= n) ? (uint32_t)i : vals_in[i];
+        if (PASS == 0) {
+            key[j] = (i < n) ? keys_in[i] : 0xffffffffu;
+            val[j] = (uint32_t)i;
+        } else {
+            const uint2 kv = (i < n) ? pairs_in[i] : make_uint2(0xffffffffu, 0u);
+            key[j] = kv.x;
+            val[j] = kv.y;
+        }
     }
-    {   // zero this warp's counters (4 KB) while the loads are in flight
-        uint4* z = reinterpret_cast<uint4*>(&s_cnt[warp][0]);
+    reinterpret_cast<uint4*>(&s_cnt[warp][0])[lane] = make_uint4(0u, 0u, 0u, 0u);   // this warp's 256 counters
+    // exclusive scan of the global digit histogram: where each digit's keys start in the output (threads < 256)
+    uint32_t gstart = 0;
+    if (tid < kRBins) {
+        const uint32_t v = ghist[PASS * kRBins + tid];
+        uint32_t incl = v;
 #pragma unroll
-        for (int k = 0; k < kBins * 2 / 16 / 32; k++) z[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        gstart = incl - v;
     }
-    block_exclusive_scan<kBins / kSortThreads>(s_start, s_scan);    // bin starts over the whole array (2 barriers inside)
-    if (PASS == 0 && block == 0 && tid == kSortThreads - 1)          // number of visible Gaussians, for the later passes
-        counters[kCntVisible] = s_start[kBins - 1] + ghist[kBins - 1];
+    __syncthreads();
+    if (tid < kRBins) {
+        for (int w = 0; w < warp; w++) gstart += s_warp[w];
+        if (PASS == 0 && block == 0 && tid == kRBins - 1)          // number of visible Gaussians, for the later passes
+            counters[kCntVisible] = gstart + ghist[kRBins - 1];
+    }
 
     // rank inside the warp's sub-chunk: all matches first (independent: eight MATCH.ANY in flight), then ONE dependent
     // sweep over the warp's counters.  Pass 0 ranks only the visible keys (culled ones are dropped here).
@@ -165,6 +188,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
         const uint32_t d = valid[j] ? ((key[j] >> shift) & mask) : 0xffffffffu;
         peers[j] = __match_any_sync(kFullMask, d);
     }
+    __syncwarp();
     uint32_t ofs[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
@@ -179,92 +203,95 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
         __syncwarp();
     }
     __syncthreads();
-    // per bin: exclusive prefix over the warps (in place), block count -> publish -> look back -> destination base
-    uint32_t agg[kBins / kSortThreads], excl[kBins / kSortThreads];
-    uint32_t* my_status = status + (size_t)block * kBins;
-#pragma unroll
-    for (int k = 0; k < kBins / kSortThreads; k++) {
-        const int b = tid + k * kSortThreads;
-        uint32_t run = 0;
+    // one digit per thread: prefix over the warps, the block's count -> publish -> local run starts -> look back
+    uint32_t agg = 0;
+    uint32_t* my_status = status + (size_t)block * kRBins;
+    if (tid < kRBins) {
 #pragma unroll
         for (int w = 0; w < kSortWarps; w++) {
-            const uint32_t t = s_cnt[w][b];
-            s_cnt[w][b] = (uint16_t)run;
-            run += t;
+            const uint32_t t = s_cnt[w][tid];
+            s_cnt[w][tid] = (uint16_t)agg;
+            agg += t;
         }
-        agg[k] = run;
-        excl[k] = 0;
-        st_status(my_status + b, (block == 0 ? tag_incl : tag_agg) | run);
+        st_status(my_status + tid, (block == 0 ? tag_incl : tag_agg) | agg);
+        uint32_t incl = agg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        s_lstart[tid] = incl - agg;     // warp-local for now
     }
-    if (block > 0) {
-        int prev[kBins / kSortThreads];
-        unsigned pending = (1u << (kBins / kSortThreads)) - 1u;
+    __syncthreads();
+    if (tid < kRBins) {
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += s_warp[w];
+        const uint32_t lstart = s_lstart[tid] + wb;
+        if (tid == kRBins - 1) s_total = lstart + agg;
+        uint32_t excl = 0;
+        int p = block - 1;
+        while (p >= 0) {   // four predecessors per step; block 0 always publishes an inclusive value
+            uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < kBins / kSortThreads; k++) prev[k] = block - 1;
-        while (pending) {
-            uint32_t v[kBins / kSortThreads];
+            for (int u = 0; u < 4; u++) v[u] = (p - u >= 0) ? ld_status(status + (size_t)(p - u) * kRBins + tid) : tag_incl;
+            int used = 0;
+            bool done = false, stalled = false;
 #pragma unroll
-            for (int k = 0; k < kBins / kSortThreads; k++)
-                v[k] = ((pending >> k) & 1u) ? ld_status(status + (size_t)prev[k] * kBins + tid + k * kSortThreads) : 0u;
-            bool stalled = false;
-#pragma unroll
-            for (int k = 0; k < kBins / kSortThreads; k++) {
-                if (!((pending >> k) & 1u)) continue;
-                const uint32_t tag = v[k] & ~kStatMask;
+            for (int u = 0; u < 4; u++) {
+                if (done || stalled) continue;
+                const uint32_t tag = v[u] & ~kStatMask;
                 if (tag == tag_incl) {
-                    excl[k] += v[k] & kStatMask;
-                    pending &= ~(1u << k);
+                    excl += v[u] & kStatMask;
+                    done = true;
                 } else if (tag == tag_agg) {
-                    excl[k] += v[k] & kStatMask;
-                    prev[k]--;
+                    excl += v[u] & kStatMask;
+                    used++;
                 } else {
                     stalled = true;
                 }
             }
-            if (stalled) __nanosleep(40);
+            if (done) break;
+            p -= used;
+            if (stalled) __nanosleep(20);
         }
-#pragma unroll
-        for (int k = 0; k < kBins / kSortThreads; k++)
-            st_status(my_status + tid + k * kSortThreads, tag_incl | (excl[k] + agg[k]));
+        if (block > 0) st_status(my_status + tid, tag_incl | (excl + agg));
+        s_lstart[tid] = lstart;
+        s_gdst[tid] = gstart + excl - lstart;   // (mod 2^32) global position = s_gdst[digit] + local slot
     }
-#pragma unroll
-    for (int k = 0; k < kBins / kSortThreads; k++) s_start[tid + k * kSortThreads] += excl[k];
     __syncthreads();
-    // scatter: position = bin start + keys of earlier blocks + keys of earlier warps + rank inside the warp
+    // reorder in shared memory: local slot = run start of the digit + keys of earlier warps + rank inside the warp
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         if (valid[j]) {
             const uint32_t d = (key[j] >> shift) & mask;
-            const uint32_t pos = s_start[d] + s_cnt[warp][d] + ofs[j];
-            keys_out[pos] = key[j];
-            vals_out[pos] = val[j];
+            s_pairs[s_lstart[d] + s_cnt[warp][d] + ofs[j]] = make_uint2(key[j], val[j]);
         }
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t i = tid; i < total; i += kSortThreads) {
+        const uint2 kv = s_pairs[i];
+        pairs_out[s_gdst[(kv.x >> shift) & mask] + i] = kv;
     }
 }
 
 template <int PASS>
-static void launch_sort_pass(const uint32_t* kin, const uint32_t* vin, int P, SortWS& w, uint32_t* counters, uint32_t* kout,
-                             uint32_t* vout, cudaStream_t s)
+static void launch_sort_pass(const uint32_t* kin, const uint2* pin, int P, SortWS& w, uint32_t* counters, uint2* pout,
+                             cudaStream_t s)
 {
-    constexpr size_t smem = (size_t)kBins * 4 + (size_t)kSortWarps * kBins * 2;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(k_sort_pass<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev] = true;
-    }
-    k_sort_pass<PASS><<<sort_chunks(P), kSortThreads, smem, s>>>(kin, vin, P, w.ghist, w.status, counters, kout, vout);
+    k_sort_pass<PASS><<<sort_chunks(P), kSortThreads, 0, s>>>(kin, pin, P, w.ghist, w.status, counters, pout);
 }
 
-// Requires counters / ghist / status zeroed and ghist filled (k_preprocess_fwd).  Result: w.keys_a / w.vals_a hold the
-// counters[kCntVisible] visible Gaussians in (depth, index) order.
+// Requires counters / ghist / status zeroed and ghist filled (k_preprocess_fwd).  Result: w.pairs_a holds the
+// counters[kCntVisible] visible Gaussians as {depth key, id} in (depth, index) order.
 void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, uint32_t* counters, cudaStream_t s)
 {
     if (P <= 0) return;
-    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.keys_a, w.vals_a, s);
-    launch_sort_pass<1>(w.keys_a, w.vals_a, P, w, counters, w.keys_b, w.vals_b, s);
-    launch_sort_pass<2>(w.keys_b, w.vals_b, P, w, counters, w.keys_a, w.vals_a, s);
+    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.pairs_b, s);
+    launch_sort_pass<1>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, s);
+    launch_sort_pass<2>(nullptr, w.pairs_a, P, w, counters, w.pairs_b, s);
+    launch_sort_pass<3>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, s);
 }
 
 // ================================================================================================
@@ -313,14 +340,14 @@ __device__ __forceinline__ void warp_for_each_instance(uint32_t packed, uint32_t
     }
 }
 
-__device__ __forceinline__ void load_rect(const uint32_t* __restrict__ perm, const ushort4* __restrict__ rects, int i,
+__device__ __forceinline__ void load_rect(const uint2* __restrict__ perm, const ushort4* __restrict__ rects, int i,
                                           int n, uint32_t& id, uint32_t& packed, uint32_t& cnt)
 {
     id = 0;
     packed = 1u << 20;
     cnt = 0;
     if (i < n) {
-        id = perm[i];
+        id = perm[i].y;
         const ushort4 r = rects[id];
         const uint32_t w = r.z - r.x, h = r.w - r.y;   // culled Gaussians store an empty rect
         cnt = w * h;
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __rest
 // (2) enumerates its instances ONCE, writing {tile, Gaussian id} records with coalesced 8-byte stores,
 // and (3) adds them to the CTA's tile histogram (row c of H).
 // Dynamic shared memory: uint32 s_hist[T], s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1].
-__global__ void __launch_bounds__(1024) k_tile_count(const uint32_t* __restrict__ perm, int per_cta,
+__global__ void __launch_bounds__(1024) k_tile_count(const uint2* __restrict__ perm, int per_cta,
                                                     const ushort4* __restrict__ rects, int gx, int T,
                                                     uint32_t* __restrict__ hist, uint2* __restrict__ stream,
                                                     uint2* __restrict__ segs, uint32_t* __restrict__ counters, uint32_t cap)
@@ -629,7 +656,7 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
 
 // `cap`: number of instances the caller's stream / point_list arrays can hold.  If the scene has more (counters[kCntR],
 // known on the device only), every kernel here returns without touching them.
-int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
+int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
                           uint2* stream, uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;

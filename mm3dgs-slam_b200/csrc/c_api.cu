@@ -102,16 +102,17 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.rec = carve<float4>(p, n * 3);
     w.rects = carve<ushort4>(p, n);
     w.depth_keys = carve<uint32_t>(p, n);
-    // counters | ghist | status are contiguous: one memset zeroes them at the start of a forward
-    w.counters = carve<uint32_t>(p, 64);
-    w.sort.ghist = carve<uint32_t>(p, 3 * 2048);
-    w.sort.status = carve<uint32_t>(p, (size_t)sort_chunks((int)n) * 2048);
+    // counters | ghist are contiguous: one small memset zeroes them at the start of a forward (the projection kernel
+    // adds to both); the sort's look-back state is zeroed by the projection kernel itself
+    w.counters = carve<uint32_t>(p, 64);          // [63] = CTA counter of the camera-gradient reduction
+    w.sort.ghist = carve<uint32_t>(p, kSortDigits * kSortBins);
     w.zero_bytes = (size_t)(p - reinterpret_cast<char*>(w.counters));
+    w.sort.status_words = (size_t)sort_chunks((int)n) * kSortBins;
+    w.sort.status = carve<uint32_t>(p, w.sort.status_words);
     w.extra_gen = carve<float>(p, n * 3);
-    w.sort.keys_a = carve<uint32_t>(p, n);
-    w.sort.vals_a = carve<uint32_t>(p, n);
-    w.sort.keys_b = carve<uint32_t>(p, n);
-    w.sort.vals_b = carve<uint32_t>(p, n);
+    w.sort.pairs_a = carve<uint2>(p, n);
+    w.sort.pairs_b = carve<uint2>(p, n);
+    w.cam_partials = carve<double>(p, (size_t)kCamPartialRows * 35);
     int ctas, per_cta, warps;
     size_t sc, ss;
     tile_partition_plan((int)n, T, ctas, per_cta, warps, sc, ss);
@@ -230,7 +231,7 @@ void gsr_geom_layout_of(int32_t P, int32_t W, int32_t H, gsr_geom_layout* o)
     o->rec = (size_t)w.rec;
     o->rects = (size_t)w.rects;
     o->depth_keys = (size_t)w.depth_keys;
-    o->sorted_ids = (size_t)w.sort.vals_a;
+    o->sorted_ids = (size_t)w.sort.pairs_a;
     o->counters = (size_t)w.counters;
     o->total = w.total;
 }
@@ -275,10 +276,11 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     a.focal_y = H / (2.0f * cam->tanfovy);
     a.focal_x = W / (2.0f * cam->tanfovx);
     a.radii = radii; a.rec = gw.rec; a.rects = gw.rects; a.depth_keys = gw.depth_keys; a.num_rendered = gw.counters + kCntR;
-    a.ghist = gw.sort.ghist;
+    a.ghist = gw.sort.ghist; a.status = gw.sort.status; a.status_words = gw.sort.status_words;
+    a.chunk_ticket = gw.counters + kCntChunkFwd;
     a.extra_gen = g->extra_mode == 1 ? gw.extra_gen : nullptr;
     prof_mark(ST_BEGIN, stream);
-    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, gw.zero_bytes, stream));   // counters + digit histograms + look-back state
+    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, gw.zero_bytes, stream));   // counters + digit histograms (4 KB)
     launch_preprocess_fwd(a, stream);
     GSR_STAGE("preprocess", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS, stream, 1);
@@ -292,7 +294,7 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     }
     launch_depth_sort(gw.depth_keys, P, gw.sort, gw.counters, stream);
     GSR_STAGE("depth_sort", cam->debug, stream);
-    GSR_MARK(ST_DEPTH_SORT, stream, 3);
+    GSR_MARK(ST_DEPTH_SORT, stream, 4);
     if (async_r) {
         GSR_CUDA(cudaEventSynchronize(hs.ev));
         *num_rendered = *hs.pinned;
@@ -331,7 +333,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (launch_tile_partition(gw.sort.vals_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters, (uint32_t)R,
+    if (launch_tile_partition(gw.sort.pairs_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters, (uint32_t)R,
                               bw.point_list, stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
@@ -387,6 +389,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     a.dL_dmeans3D = gr->dL_dmeans3D; a.dL_dcov3D = gr->dL_dcov3D; a.dL_dsh = gr->dL_dsh;
     a.dL_dscales = gr->dL_dscales; a.dL_drots = gr->dL_drotations;
     a.dL_dview = gr->dL_dviewmatrix; a.dL_dproj = gr->dL_dprojmatrix; a.dL_dcampos = gr->dL_dcampos;
+    a.cam_partials = gw.cam_partials; a.cam_done = gw.counters + 63; a.chunk_ticket = gw.counters + kCntChunkBwd;
     a.accumulate = gr->accumulate;
     a.dL_dextra_gen = g->extra_mode == 1 ? gr->dL_dextra : nullptr;
     launch_preprocess_bwd(a, stream);

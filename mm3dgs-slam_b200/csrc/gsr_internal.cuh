@@ -23,18 +23,25 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 constexpr int kCntR = 0;         // number of tile instances (num_rendered)
 constexpr int kCntClaim = 1;     // tile partition: next free slot of the instance stream
 constexpr int kCntVisible = 2;   // number of visible Gaussians (= length of the depth-sorted list)
-constexpr int kCntTicket = 3;    // [3] block tickets of the three depth-sort passes
+constexpr int kCntTicket = 3;    // [4] block tickets of the four depth-sort passes (slots 3..6)
+constexpr int kCntChunkFwd = 8;  // chunk ticket of k_preprocess_fwd
+constexpr int kCntChunkBwd = 9;  // chunk ticket of k_preprocess_bwd (wraps to zero by itself)
+constexpr int kSortDigits = 4;   // 8-bit digits of the depth sort
+constexpr int kSortBins = 256;
 
 struct SortWS {
-    uint32_t *keys_a, *vals_a, *keys_b, *vals_b;   // depth-sort ping-pong (P each); result in keys_a / vals_a
-    uint32_t* ghist;                               // [3][2048] global digit histograms of the visible depth keys
-    uint32_t* status;                              // [sort_chunks(P)][2048] look-back state of the sort passes
+    uint2 *pairs_a, *pairs_b;                      // depth-sort ping-pong of {depth key, Gaussian id} (P each); result in pairs_a
+    uint32_t* ghist;                               // [4][256] global digit histograms of the visible depth keys
+    uint32_t* status;                              // [sort_chunks(P)][256] look-back state of the sort passes
+    size_t status_words;
     uint32_t* tile_hist;                           // [partition CTAs][T]
     uint32_t* tile_totals;                         // [T]
     uint32_t* tile_starts;                         // [T]
     uint2* segs;                                   // [partition CTAs * warps] {stream offset, length}
 };
+constexpr int kCamPartialRows = 1024;   // >= the grid of k_preprocess_bwd (2 CTAs per SM)
 struct GeomWS {
+    double* cam_partials;  // [kCamPartialRows][35] scratch of the camera-gradient reduction
     float4* rec;
     ushort4* rects;        // tile rectangle {x0, y0, x1, y1}; empty for culled Gaussians
     uint32_t* depth_keys;  // float bits of the view depth; 0xFFFFFFFF for culled Gaussians
@@ -73,7 +80,10 @@ struct PreArgs {
     ushort4* rects;
     uint32_t* depth_keys;
     uint32_t* num_rendered;   // device counter, zeroed by the caller
-    uint32_t* ghist;          // [3][2048] digit histograms of the visible depth keys (11/11/10 bits), zeroed by the caller
+    uint32_t* ghist;          // [4][256] digit histograms of the visible depth keys (8 bits each), zeroed by the caller
+    uint32_t* status;         // look-back state of the depth sort: zeroed by this kernel (status_words u32)
+    size_t status_words;
+    uint32_t* chunk_ticket;   // chunk scheduler of the persistent kernel, zeroed by the caller
     float* extra_gen;         // [P,3] generated depth/silhouette colours (z, 1, z^2), or nullptr
 };
 void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s);
@@ -81,7 +91,7 @@ void launch_mark_visible(int P, const float* means, const float* view, const flo
                          cudaStream_t s);
 
 void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, uint32_t* counters, cudaStream_t s);
-int launch_tile_partition(const uint32_t* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
+int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
                           uint2* stream, uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s);
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
@@ -105,6 +115,9 @@ struct PreBwdArgs {
     const float* dL_dcolors;  // [P,3]
     float *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots;
     float *dL_dview, *dL_dproj, *dL_dcampos;
+    double* cam_partials;     // [kCamPartialRows][35] per-CTA fp64 partial sums of the camera gradients (geometry workspace)
+    unsigned* cam_done;       // CTAs that have written their record (zero on entry, reset by the kernel)
+    unsigned* chunk_ticket;   // chunk scheduler of the persistent kernel (zero on entry; wraps back to zero by itself)
     int accumulate;
     const float* dL_dextra_gen;   // [P,3] gradient of the generated (z, 1, z^2) colours, or nullptr
 };

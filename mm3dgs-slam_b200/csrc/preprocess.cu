@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_raw + 2 * sizeof(FwdIn) + 2 * sizeof(FwdOut));
     __shared__ float s_cam[35];
     __shared__ uint32_t s_tiles;
+    __shared__ int s_chunk[2];                            // chunk index of each stage (tickets: dynamic scheduling)
+    __shared__ uint32_t s_hist[kSortDigits * kSortBins];  // this CTA's share of the depth sort's digit histograms
 
     const int tid = threadIdx.x;
     const bool has_sr = (a.cov3D_pre == nullptr);
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
-    __syncthreads();
+    for (int i = tid; i < kSortDigits * kSortBins; i += kPB) s_hist[i] = 0u;
 
     const uint32_t stage_bytes = (uint32_t)sizeof(float) * kPB * (3 + 1) + (has_sr ? (uint32_t)sizeof(float) * kPB * 7 : 0u) +
                                  (col_staged ? (uint32_t)sizeof(float) * kPB * 3 : 0u);
@@ -74,18 +76,33 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
         }
         if (col_staged) bulk_g2s(in.col, (sh_path ? a.shs : a.colors) + b * 3, sizeof(float) * kPB * 3, &s_full[st]);
     };
-    if (tid == 0 && (int)blockIdx.x < nchunks && is_bulk(blockIdx.x)) issue(blockIdx.x, 0);
+    // chunks are handed out by a ticket counter, one chunk ahead of the math: no CTA is left with a longer static share
+    if (tid == 0) {
+        const int c0 = (int)atomicAdd(a.chunk_ticket, 1u);
+        s_chunk[0] = c0;
+        if (c0 < nchunks && is_bulk(c0)) issue(c0, 0);
+    }
+    __syncthreads();
+    {   // zero this CTA's slice of the depth sort's look-back state (consumed by the kernels that follow)
+        uint4* z = reinterpret_cast<uint4*>(a.status);
+        const size_t n4 = a.status_words >> 2;
+        for (size_t i = (size_t)blockIdx.x * kPB + tid; i < n4; i += (size_t)gridDim.x * kPB) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
 
     uint32_t my_tiles = 0;
-    int it = 0;
-    for (int c = blockIdx.x; c < nchunks; c += gridDim.x, it++) {
+    for (int it = 0;; it++) {
         const int st = it & 1;
+        const int c = s_chunk[st];
+        if (c >= nchunks) break;
         FwdIn& in = s_in[st];
         FwdOut& out = s_out[st];
         const int base = c * kPB;
         const int nb = min(kPB, a.P - base);
-        const int nxt = c + gridDim.x;
-        if (tid == 0 && nxt < nchunks && is_bulk(nxt)) issue(nxt, st ^ 1);
+        if (tid == 0) {   // the other stage was last read in iteration it-1, which every thread left through two barriers
+            const int nxt = (int)atomicAdd(a.chunk_ticket, 1u);
+            s_chunk[st ^ 1] = nxt;
+            if (nxt < nchunks && is_bulk(nxt)) issue(nxt, st ^ 1);
+        }
         if (is_bulk(c)) {
             mbar_wait(&s_full[st], (uint32_t)((it >> 1) & 1));
         } else {   // ragged last chunk / unaligned arrays
@@ -130,11 +147,16 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
                 float cr, cg, cb;
                 int bits = 0;
                 if (sh_path) {
-                    V3 dir = {p.x - s_cam[32], p.y - s_cam[33], p.z - s_cam[34]};
-                    float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-                    dir.x = dir.x / len;
-                    dir.y = dir.y / len;
-                    dir.z = dir.z / len;
+                    V3 dir = {0.f, 0.f, 1.f};
+                    if (a.D > 0) {   // degree 0 has no view dependence: skip the normalisation (three IEEE divisions + a root)
+                        dir.x = p.x - s_cam[32];
+                        dir.y = p.y - s_cam[33];
+                        dir.z = p.z - s_cam[34];
+                        float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+                        dir.x = dir.x / len;
+                        dir.y = dir.y / len;
+                        dir.z = dir.z / len;
+                    }
                     const float* sh = (a.M == 1) ? (in.col + 3 * tid) : (a.shs + (size_t)idx * a.M * 3);
                     V3 cc = sh_to_rgb(a.D, sh, dir);
                     bits = (cc.x < 0 ? 1 : 0) | (cc.y < 0 ? 2 : 0) | (cc.z < 0 ? 4 : 0);
@@ -165,17 +187,19 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
                 a.extra_gen[(size_t)idx * 3 + 2] = z * z;
             }
         }
-        {   // digit histograms of the depth sort (11 / 11 / 10 bits), while the key is in a register: fire-and-forget
-            // REDs; the low digits are mantissa bits (spread over 2048 addresses), the top digit (sign, exponent, one
-            // mantissa bit) takes a handful of values, so it is aggregated over the warp first
+        {   // digit histograms of the depth sort (four 8-bit digits), while the key is in a register: shared-memory
+            // atomics, flushed once per CTA.  The two low digits are mantissa bits (spread over the 256 counters); the
+            // two high ones (exponent, top mantissa bits) take few values inside a warp, so they are aggregated first.
             const bool v = dkey != 0xffffffffu;
             if (v) {
-                atomicAdd(&a.ghist[dkey & 2047u], 1u);
-                atomicAdd(&a.ghist[2048u + ((dkey >> 11) & 2047u)], 1u);
+                atomicAdd(&s_hist[dkey & 255u], 1u);
+                atomicAdd(&s_hist[256u + ((dkey >> 8) & 255u)], 1u);
             }
-            const uint32_t d2 = v ? (dkey >> 22) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(0xffffffffu, d2);
-            if (v && (tid & 31) == __ffs(peers) - 1) atomicAdd(&a.ghist[4096u + d2], (uint32_t)__popc(peers));
+            const int lane_ = tid & 31;
+            const uint32_t d2 = v ? ((dkey >> 16) & 255u) : 0xffffffffu, d3 = v ? (dkey >> 24) : 0xffffffffu;
+            const unsigned p2 = __match_any_sync(0xffffffffu, d2), p3 = __match_any_sync(0xffffffffu, d3);
+            if (v && lane_ == __ffs(p2) - 1) atomicAdd(&s_hist[512u + d2], (uint32_t)__popc(p2));
+            if (v && lane_ == __ffs(p3) - 1) atomicAdd(&s_hist[768u + d3], (uint32_t)__popc(p3));
         }
         // the bulk store issued two iterations ago has finished reading this output stage
         if (tid == 0) bulk_wait_read<1>();
@@ -202,6 +226,10 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
         if ((tid & 31) == 0 && wsum) atomicAdd(&s_tiles, wsum);
         __syncthreads();
         if (tid == 0 && s_tiles) atomicAdd(a.num_rendered, s_tiles);
+        for (int i = tid; i < kSortDigits * kSortBins; i += kPB) {
+            const uint32_t h = s_hist[i];
+            if (h) atomicAdd(&a.ghist[i], h);
+        }
     }
 }
 

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
     BwdOut* s_out = reinterpret_cast<BwdOut*>(s_raw + 2 * sizeof(BwdIn));
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_raw + 2 * sizeof(BwdIn) + 2 * sizeof(BwdOut));
     __shared__ float s_cam[35];
-    __shared__ float s_red[CAM ? (kPB / 32) * 35 : 1];
+    __shared__ int s_chunk[2];   // chunk index of each stage (tickets: dynamic scheduling)
 
     const int tid = threadIdx.x;
     const bool has_sr = (a.scales != nullptr);
@@ -92,18 +92,29 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
         for (int k = 0; k < 35; k++) cam[k] = 0.f;
     }
 
-    if (tid == 0 && (int)blockIdx.x < nchunks && is_bulk(blockIdx.x)) issue(blockIdx.x, 0);
+    // Chunks are handed out by a ticket counter, one chunk ahead of the math.  Every CTA draws exactly one ticket past
+    // the end, so a launch draws nchunks + gridDim.x tickets: atomicInc with that period leaves the counter at zero.
+    const unsigned ticket_wrap = (unsigned)nchunks + gridDim.x - 1u;
+    if (tid == 0) {
+        const int c0 = (int)atomicInc(a.chunk_ticket, ticket_wrap);
+        s_chunk[0] = c0;
+        if (c0 < nchunks && is_bulk(c0)) issue(c0, 0);
+    }
+    __syncthreads();
 
-    int it = 0;
-    for (int c = blockIdx.x; c < nchunks; c += gridDim.x, it++) {
+    for (int it = 0;; it++) {
         const int st = it & 1;
+        const int c = s_chunk[st];
+        if (c >= nchunks) break;
         BwdIn& in = s_in[st];
         BwdOut& out = s_out[st];
         const int base = c * kPB;
         const int nb = min(kPB, a.P - base);
-        const int nxt = c + gridDim.x;
-        // the other stage was last read in iteration it-1, which every thread left through two barriers
-        if (tid == 0 && nxt < nchunks && is_bulk(nxt)) issue(nxt, st ^ 1);
+        if (tid == 0) {   // the other stage was last read in iteration it-1, which every thread left through two barriers
+            const int nxt = (int)atomicInc(a.chunk_ticket, ticket_wrap);
+            s_chunk[st ^ 1] = nxt;
+            if (nxt < nchunks && is_bulk(nxt)) issue(nxt, st ^ 1);
+        }
         if (is_bulk(c)) {
             mbar_wait(&s_full[st], (uint32_t)((it >> 1) & 1));
         } else {   // ragged last chunk / unaligned arrays: synchronous staging
@@ -279,21 +290,39 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
     if (tid == 0) bulk_wait_read<0>();   // shared memory must outlive the stores that read it
 
     if (CAM) {
+        // Camera gradients: 35 sums over all Gaussians, with heavy cancellation (the rotation terms).  Per-thread fp32
+        // partials (a few Gaussians each) are folded in fp64: warp -> CTA -> one record per CTA, and the last CTA to
+        // finish adds the records up in index order, so the result does not depend on the order CTAs ran in.
+        double (*s_red)[35] = reinterpret_cast<double (*)[35]>(s_raw);     // the staging buffers are free now
+        __syncthreads();
         const int w = tid >> 5, l = tid & 31;
 #pragma unroll
         for (int k = 0; k < 35; k++) {
-            const float v = warp_sum(cam[k]);
-            if (l == 0) s_red[w * 35 + k] = v;
+            double v = (double)cam[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (l == 0) s_red[w][k] = v;
         }
         __syncthreads();
         if (tid < 35) {
-            float v = 0.f;
+            double v = 0.0;
 #pragma unroll
-            for (int w2 = 0; w2 < kPB / 32; w2++) v += s_red[w2 * 35 + tid];
+            for (int w2 = 0; w2 < kPB / 32; w2++) v += s_red[w2][tid];
+            a.cam_partials[(size_t)blockIdx.x * 35 + tid] = v;
+        }
+        __threadfence();
+        __syncthreads();
+        __shared__ unsigned s_last;
+        if (tid == 0) s_last = (atomicAdd(a.cam_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last && tid < 35) {
+            double v = 0.0;
+            for (unsigned c = 0; c < gridDim.x; c++) v += __ldcg(&a.cam_partials[(size_t)c * 35 + tid]);
             float* dst = tid < 16 ? (a.dL_dview ? a.dL_dview + tid : nullptr)
                        : tid < 32 ? (a.dL_dproj ? a.dL_dproj + (tid - 16) : nullptr)
                                   : (a.dL_dcampos ? a.dL_dcampos + (tid - 32) : nullptr);
-            if (dst != nullptr && v != 0.f) atomicAdd(dst, v);
+            if (dst != nullptr) *dst += (float)v;     // (acc) buffer: the caller's contents are kept
+            if (tid == 0) *a.cam_done = 0u;           // ready for the next launch on this workspace
         }
     }
 }
@@ -316,7 +345,7 @@ void launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
     if (a.P <= 0) return;
     const bool cam = a.dL_dview || a.dL_dproj || a.dL_dcampos;
     const int nchunks = (a.P + kPB - 1) / kPB;
-    const int grid = min(nchunks, 2 * device_sm_count());
+    const int grid = min(min(nchunks, 2 * device_sm_count()), kCamPartialRows);
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool sh1 = a.shs != nullptr && a.M == 1;
     const int bulk_ok = al(a.rec) && al(a.means) && al(a.dL_dmean2D) && al(a.dL_dconic) && al(a.dL_dmeans3D) &&

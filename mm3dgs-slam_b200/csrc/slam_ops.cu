@@ -29,6 +29,8 @@ struct LossArgs {
     float* dmaps;        // [3 maps][3][H][W]: A = dS/dmu1 (total), B = dS/dE11, C = dS/dE12
     double* partials;    // [CTAs][kNPart]
     float* stats;        // [kNStat]
+    float* colstats;     // [W][4] per image column: xbar, ybar, ka, kb (GSR_DEPTH_PEARSON_COLS)
+    double* col_loss;    // [W]    per image column: 1 - r
     float* losses;       // [4]
     float *dL_dimage, *dL_ddimg;
     SsimWin win;
@@ -194,6 +196,48 @@ __global__ void __launch_bounds__(kLT, 5) k_loss_fwd(const LossArgs a)
     }
 }
 
+// ---- GSR_DEPTH_PEARSON_COLS: one correlation coefficient per image column -----------------------------------
+// A CTA owns 32 adjacent columns; lane = column (128-byte row segments), the 8 warps stride over the rows.  Sums in
+// double, folded over the warps in a fixed order (bit-reproducible).  Writes per column: 1 - r and the four scalars
+// the gradient needs:  d(1 - r_c)/dx_i = ka_c (y_i - ybar_c) + kb_c (x_i - xbar_c), already scaled by
+// grad_scale * depth_weight / W.
+__global__ void __launch_bounds__(256) k_pearson_cols(const LossArgs a)
+{
+    __shared__ double s_acc[8][5][32];
+    const int W = a.c.width, H = a.c.height;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (x < W)
+        for (int y = warp; y < H; y += 8) {
+            const double xv = a.dimg[(size_t)y * W + x], yv = a.dtarget[(size_t)y * W + x];
+            acc[0] += xv; acc[1] += yv; acc[2] += xv * xv; acc[3] += yv * yv; acc[4] += xv * yv;
+        }
+#pragma unroll
+    for (int j = 0; j < 5; j++) s_acc[warp][j][lane] = acc[j];
+    __syncthreads();
+    if (warp != 0 || x >= W) return;
+    double d[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v += s_acc[w][j][lane];
+        d[j] = v;
+    }
+    const double n = (double)H;
+    const double xbar = d[0] / n, ybar = d[1] / n;
+    const double sxx = d[2] - d[0] * d[0] / n, syy = d[3] - d[1] * d[1] / n, sxy = d[4] - d[0] * d[1] / n;
+    const double r = sxy / sqrt(sxx * syy);
+    const bool clamped = (r > 1.0) || (r < -1.0);
+    a.col_loss[x] = 1.0 - fmin(fmax(r, -1.0), 1.0);
+    const double k = clamped ? 0.0 : (double)a.c.grad_scale * (double)a.c.depth_weight / (double)W;
+    a.colstats[4 * x + 0] = (float)xbar;
+    a.colstats[4 * x + 1] = (float)ybar;
+    a.colstats[4 * x + 2] = (float)(-k / sqrt(sxx * syy));
+    a.colstats[4 * x + 3] = (float)(k * r / sxx);
+}
+
 // ---- pass 2: one CTA folds the partials in a fixed order and derives every scalar the gradient needs ------
 constexpr int kFinT = 1024;   // the finalize CTA: latency-bound walk over the partial records, so as wide as a CTA gets
 __global__ void __launch_bounds__(kFinT) k_loss_finalize(const LossArgs a, int n_tiles)
@@ -275,6 +319,11 @@ __global__ void __launch_bounds__(kFinT) k_loss_finalize(const LossArgs a, int n
         st[kStKa] = (float)(-k * sign / sqrt(sxx * syy));
         st[kStKb] = (float)(k * r / sxx);
         st[kStVariant] = (float)variant;
+    }
+    if (c.depth_mode == GSR_DEPTH_PEARSON_COLS) {   // mean over the columns, in a fixed order
+        double sum = 0.0;
+        for (int x = 0; x < c.width; x++) sum += a.col_loss[x];
+        depth = sum / (double)c.width;
     }
     for (int j = 0; j < kNStat; j++) a.stats[j] = st[j];
     a.losses[0] = (float)((double)c.color_weight * color + (double)c.depth_weight * depth);
@@ -367,6 +416,9 @@ __global__ void __launch_bounds__(kLT) k_loss_bwd(const LossArgs a)
                 const float x = a.dimg[pix], y = a.dtarget[pix];
                 if (a.c.depth_mode == GSR_DEPTH_L1_MEAN || a.c.depth_mode == GSR_DEPTH_L1_SUM) {
                     g = k_l1 * sgn(x - y);
+                } else if (a.c.depth_mode == GSR_DEPTH_PEARSON_COLS) {
+                    const float4 cs = reinterpret_cast<const float4*>(a.colstats)[gx];
+                    g = cs.z * (y - cs.y) + cs.w * (x - cs.x);
                 } else {
                     const float yv = variant == 2 ? 1.f / (y + 200.f) : y;   // variant 1's sign lives in ka
                     g = ka * (yv - ybar) + kb * (x - xbar);
@@ -438,7 +490,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ params, float*
     }
 }
 
-struct LossWS { float* dmaps; double* partials; float* stats; size_t total; };
+struct LossWS { float* dmaps; double* partials; float* stats; float* colstats; double* col_loss; size_t total; };
 static LossWS loss_ws_carve(char* base, int W, int H)
 {
     LossWS w;
@@ -447,6 +499,8 @@ static LossWS loss_ws_carve(char* base, int W, int H)
     w.dmaps = (float*)(base + off);      off = align_up(off + (size_t)9 * W * H * sizeof(float), 256);
     w.partials = (double*)(base + off);  off = align_up(off + tiles * 4 * kNPart * sizeof(double), 256);
     w.stats = (float*)(base + off);      off = align_up(off + kNStat * sizeof(float), 256);
+    w.colstats = (float*)(base + off);   off = align_up(off + (size_t)W * 4 * sizeof(float), 256);
+    w.col_loss = (double*)(base + off);  off = align_up(off + (size_t)W * sizeof(double), 256);
     w.total = off;
     return w;
 }
@@ -471,8 +525,10 @@ int gsr_slam_loss(gsr_stream_t stream_, const gsr_loss_config* cfg, const float*
     if (!cfg || !losses) return api_fail(GSR_ERR_INVALID, "null config / losses");
     if (cfg->width <= 0 || cfg->height <= 0) return api_fail(GSR_ERR_INVALID, "image size must be positive");
     if (cfg->color_mode < GSR_COLOR_NONE || cfg->color_mode > GSR_COLOR_MASKED_L1_SUM ||
-        cfg->depth_mode < GSR_DEPTH_NONE || cfg->depth_mode > GSR_DEPTH_PEARSON_INV)
+        cfg->depth_mode < GSR_DEPTH_NONE || cfg->depth_mode > GSR_DEPTH_PEARSON_COLS)
         return api_fail(GSR_ERR_INVALID, "unknown colour / depth loss mode");
+    if (cfg->depth_mode == GSR_DEPTH_PEARSON_COLS && cfg->depth_mask != 0)
+        return api_fail(GSR_ERR_INVALID, "GSR_DEPTH_PEARSON_COLS is the unmasked form: depth_mask must be 0");
     if ((cfg->color_mask | cfg->depth_mask) & ~7) return api_fail(GSR_ERR_INVALID, "unknown mask flag");
     const bool masked_color = cfg->color_mode == GSR_COLOR_MASKED_L1_MEAN || cfg->color_mode == GSR_COLOR_MASKED_L1_SUM;
     const int used_masks = (masked_color ? cfg->color_mask : 0) | (cfg->depth_mode != GSR_DEPTH_NONE ? cfg->depth_mask : 0);
@@ -493,6 +549,7 @@ int gsr_slam_loss(gsr_stream_t stream_, const gsr_loss_config* cfg, const float*
     a.c = *cfg;
     a.image = image; a.dimg = depth_image; a.gt_color = gt_color; a.dtarget = depth_target; a.gt_depth = gt_depth;
     a.dmaps = w.dmaps; a.partials = w.partials; a.stats = w.stats; a.losses = losses;
+    a.colstats = w.colstats; a.col_loss = w.col_loss;
     a.dL_dimage = dL_dimage; a.dL_ddimg = dL_ddepth_image;
     {   // R/utils/loss_utils.py:98-105: float32 tensor of exp(-(x-5)^2 / (2 sigma^2)), divided by its float32 sum
         float g[2 * kWR + 1], sum = 0.f;
@@ -502,8 +559,12 @@ int gsr_slam_loss(gsr_stream_t stream_, const gsr_loss_config* cfg, const float*
     const int tx = (cfg->width + kTW - 1) / kTW, ty = (cfg->height + kTH - 1) / kTH;
     const dim3 grid(tx, ty, 4);
     k_loss_fwd<<<grid, kLT, 0, stream>>>(a);
-    k_loss_finalize<<<1, kFinT, 0, stream>>>(a, tx * ty);
     int launches = 2;
+    if (cfg->depth_mode == GSR_DEPTH_PEARSON_COLS) {
+        k_pearson_cols<<<(cfg->width + 31) / 32, 256, 0, stream>>>(a);
+        launches++;
+    }
+    k_loss_finalize<<<1, kFinT, 0, stream>>>(a, tx * ty);
     if (want_grad) {
         k_loss_bwd<<<grid, kLT, 0, stream>>>(a);   // CTAs of an image without a gradient buffer return at once
         launches++;

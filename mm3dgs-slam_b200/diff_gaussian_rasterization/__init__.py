@@ -160,6 +160,12 @@ class _GeomLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in ("rec", "rects", "depth_keys", "sorted_ids", "counters", "total")]
 
 
+class _Count(int):
+    """Instance count of a forward: the true number of tile instances (compares like an int), with the capacity the
+    binning workspace was carved with in `.cap` (what gsr_backward must be given; cap >= count)."""
+    cap = 0
+
+
 class _SlotPool:
     """Pinned int32 slots for the device->host hand-off of the instance count R (cudaHostAlloc is far too slow to
     call per frame).  A slot is handed out once and comes back when its consumer has read it, so any number of
@@ -281,8 +287,8 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
 def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
                     extra=None, prepared=None):
     """Returns (R, color, radii, geom, binning, img); with `extra` ([P,3] colours) the 7th element is the
-    extra [3,H,W] image blended in the same pass.  R is the capacity the binning workspace was carved with (what
-    gsr_backward needs); it is >= the true instance count.
+    extra [3,H,W] image blended in the same pass.  R is a _Count: the true instance count, with the capacity the
+    binning workspace was carved with (what gsr_backward needs) in R.cap.
 
     The host never waits for the GPU to drain: phase 2 is enqueued against a capacity ESTIMATE of the instance list
     (the largest count seen for this problem size, plus a margin) right behind phase 1, and only then does the host
@@ -302,7 +308,7 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
         color.zero_()
         e = torch.empty(0, **u8)
         radii = torch.empty((0,), dtype=torch.int32, device=dev)
-        return (0, color, radii, e, e, e) + ((torch.zeros_like(color),) if extra is not None else ())
+        return (_Count(0), color, radii, e, e, e) + ((torch.zeros_like(color),) if extra is not None else ())
     R = None
     if prepared is not None:
         key = _input_key((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, view, proj, campos,
@@ -352,7 +358,9 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
     if R > cap:
         cap = R
         binning = render(cap)
-    return (cap, color, radii, geom, binning, img) + ((extra_img,) if has_extra else ())
+    R = _Count(R)
+    R.cap = cap
+    return (R, color, radii, geom, binning, img) + ((extra_img,) if has_extra else ())
 
 
 def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view,
@@ -460,7 +468,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         num_rendered, color, radii, geom, binning, img = out[:6]
         extra_img = out[6] if len(out) > 6 else None
         ctx.raster_settings = rs
-        ctx.num_rendered = num_rendered
+        ctx.num_rendered = int(num_rendered.cap)     # the capacity the binning workspace was carved with
         ctx.has_extra = extra_img is not None
         ctx.extra_gen = isinstance(extra_, str)
         ctx.save_for_backward(means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_, radii,

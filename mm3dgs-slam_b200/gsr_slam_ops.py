@@ -21,7 +21,7 @@ import torch
 from diff_gaussian_rasterization import _check, _lib
 
 COLOR_NONE, COLOR_L1_SSIM, COLOR_MASKED_L1_MEAN, COLOR_MASKED_L1_SUM = 0, 1, 2, 3
-DEPTH_NONE, DEPTH_L1_MEAN, DEPTH_L1_SUM, DEPTH_PEARSON, DEPTH_PEARSON_INV = 0, 1, 2, 3, 4
+DEPTH_NONE, DEPTH_L1_MEAN, DEPTH_L1_SUM, DEPTH_PEARSON, DEPTH_PEARSON_INV, DEPTH_PEARSON_COLS = 0, 1, 2, 3, 4, 5
 MASK_GT_DEPTH_POS, MASK_NOT_NAN, MASK_SILHOUETTE = 1, 2, 4
 ADAM_MAX_SEGMENTS = 16
 
@@ -56,8 +56,12 @@ def mapper_splatam(lambda_dssim=0.2):
 
 
 def mapper_default(lambda_dssim=0.2, pearson_weight=0.05, use_gt_depth=False):
-    """(1-l) L1 + l (1 - SSIM) + w * pearson_loss(depth, est or gt, invert_estimate=False)   (R/slam/mapper.py:862-885)"""
-    return dict(color_mode=COLOR_L1_SSIM, lambda_dssim=lambda_dssim, depth_mode=DEPTH_PEARSON,
+    """(1-l) L1 + l (1 - SSIM) + w * pearson_loss(depth, est or gt, invert_estimate=False)   (R/slam/mapper.py:862-885).
+    Without ground-truth depth the reference passes mask=None, so torchmetrics sees the 2-D [H, W] images and returns one
+    coefficient per image column (averaged by the trailing .mean()): DEPTH_PEARSON_COLS.  With ground-truth depth the
+    masked, flattened pixels give one global coefficient: DEPTH_PEARSON."""
+    return dict(color_mode=COLOR_L1_SSIM, lambda_dssim=lambda_dssim,
+                depth_mode=DEPTH_PEARSON if use_gt_depth else DEPTH_PEARSON_COLS,
                 depth_mask=MASK_GT_DEPTH_POS if use_gt_depth else 0, color_weight=1.0, depth_weight=pearson_weight)
 
 

@@ -65,18 +65,22 @@ def ssim(a, b, window_size=11):
 
 
 def pearson_corrcoef(preds, target):
-    """Published definition (see the module docstring); 1-D inputs."""
-    n = preds.numel()
-    mx, my = preds.mean(), target.mean()
-    var_x = ((preds - mx) ** 2).sum() / (n - 1)
-    var_y = ((target - my) ** 2).sum() / (n - 1)
-    cov = ((preds - mx) * (target - my)).sum() / (n - 1)
+    """Published definition (see the module docstring).  1-D inputs: one coefficient.  2-D inputs [N, d]: torchmetrics
+    treats dim 0 as the N samples and dim 1 as d independent outputs and returns d coefficients — which is what the
+    reference's UNMASKED call gets, because it passes the [H, W] depth images as they are (R/utils/loss_utils.py:52-53,
+    called with mask=None from R/slam/mapper.py:862-868): one coefficient per image column."""
+    n = preds.shape[0]
+    mx, my = preds.mean(0), target.mean(0)
+    var_x = ((preds - mx) ** 2).sum(0) / (n - 1)
+    var_y = ((target - my) ** 2).sum(0) / (n - 1)
+    cov = ((preds - mx) * (target - my)).sum(0) / (n - 1)
     return torch.clamp(cov / (var_x * var_y).sqrt(), -1.0, 1.0)
 
 
 def pearson_loss(render, estimate, mask=None, invert_estimate=True):
-    r = render[mask] if mask is not None else render.reshape(-1)
-    e = estimate[mask] if mask is not None else estimate.reshape(-1)
+    """mask=None keeps the 2-D images (per-column coefficients, averaged by the trailing .mean()), like the reference."""
+    r = render[mask] if mask is not None else render
+    e = estimate[mask] if mask is not None else estimate
     if invert_estimate:
         a = (1 - pearson_corrcoef(-e, r)).mean()
         b = (1 - pearson_corrcoef(1 / (e + 200.0), r)).mean()
@@ -86,7 +90,7 @@ def pearson_loss(render, estimate, mask=None, invert_estimate=True):
 
 # ---- the C-ABI's configuration space, restated with the functions above ------------------------------------
 COLOR_NONE, COLOR_L1_SSIM, COLOR_MASKED_L1_MEAN, COLOR_MASKED_L1_SUM = 0, 1, 2, 3
-DEPTH_NONE, DEPTH_L1_MEAN, DEPTH_L1_SUM, DEPTH_PEARSON, DEPTH_PEARSON_INV = 0, 1, 2, 3, 4
+DEPTH_NONE, DEPTH_L1_MEAN, DEPTH_L1_SUM, DEPTH_PEARSON, DEPTH_PEARSON_INV, DEPTH_PEARSON_COLS = 0, 1, 2, 3, 4, 5
 MASK_GT_DEPTH_POS, MASK_NOT_NAN, MASK_SILHOUETTE = 1, 2, 4
 
 
@@ -125,6 +129,8 @@ def slam_loss(cfg, image, depth_image, gt_color, depth_target, gt_depth):
             depth = torch.abs(depth_target - x)[mask].mean()
         elif dm == DEPTH_L1_SUM:
             depth = torch.abs(depth_target - x)[mask].sum()
+        elif dm == DEPTH_PEARSON_COLS:     # the reference's mask=None call: 2-D images, one coefficient per column
+            depth = pearson_loss(x, depth_target, mask=None, invert_estimate=False)
         else:
             depth = pearson_loss(x, depth_target, mask=mask, invert_estimate=(dm == DEPTH_PEARSON_INV))
     total = cfg.get("color_weight", 1.0) * color + cfg.get("depth_weight", 1.0) * depth
@@ -138,7 +144,8 @@ def mapper_splatam(lambda_dssim=0.2):          # R/slam/mapper.py:839-860
 
 
 def mapper_default(lambda_dssim=0.2, pearson_weight=0.05, use_gt_depth=False):   # R/slam/mapper.py:862-885
-    return dict(color_mode=COLOR_L1_SSIM, lambda_dssim=lambda_dssim, depth_mode=DEPTH_PEARSON,
+    return dict(color_mode=COLOR_L1_SSIM, lambda_dssim=lambda_dssim,
+                depth_mode=DEPTH_PEARSON if use_gt_depth else DEPTH_PEARSON_COLS,
                 depth_mask=MASK_GT_DEPTH_POS if use_gt_depth else 0, color_weight=1.0, depth_weight=pearson_weight)
 
 

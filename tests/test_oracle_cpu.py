@@ -84,3 +84,28 @@ def test_pearson_restatement_matches_scipy():
     a = 1 - LO.pearson_corrcoef(-est, x)
     b = 1 - LO.pearson_corrcoef(1 / (est + 200.0), x)
     assert float(LO.pearson_loss(x, est, invert_estimate=True)) == float(min(a, b))
+
+
+def test_pearson_unmasked_is_per_column():
+    """The reference's unmasked pearson_loss (R/utils/loss_utils.py:52-53,60 called with mask=None from
+    R/slam/mapper.py:862-868) hands torchmetrics the 2-D [H, W] images: H samples of W outputs, one coefficient per
+    image column, averaged by the trailing .mean().  The oracle restates exactly that; scipy per column is the check."""
+    from scipy import stats
+
+    from oracle import loss_oracle as LO
+    g = torch.Generator().manual_seed(4)
+    H, W = 24, 9
+    x = torch.randn(H, W, generator=g, dtype=torch.float64)
+    y = 0.5 * x + torch.randn(H, W, generator=g, dtype=torch.float64)
+    r = LO.pearson_corrcoef(y, x)
+    assert r.shape == (W,)
+    want = [stats.pearsonr(y[:, c].numpy(), x[:, c].numpy())[0] for c in range(W)]
+    assert float((r - torch.tensor(want)).abs().max()) < 1e-12
+    loss = float(LO.pearson_loss(x, y, mask=None, invert_estimate=False))
+    assert abs(loss - (1 - sum(want) / W)) < 1e-12
+    # ... and it is NOT the coefficient of the flattened images
+    flat = 1 - stats.pearsonr(y.reshape(-1).numpy(), x.reshape(-1).numpy())[0]
+    assert abs(loss - flat) > 1e-4
+    cfg = LO.mapper_default(use_gt_depth=False)
+    assert cfg["depth_mode"] == LO.DEPTH_PEARSON_COLS and cfg["depth_mask"] == 0
+

@@ -38,7 +38,7 @@ def decode_geom(geom, P, W, H):
                 clamped=torch.stack([(bits & 1) != 0, (bits & 2) != 0, (bits & 4) != 0], -1),
                 rects=rects, tiles_touched=(rects[:, 2] - rects[:, 0]) * (rects[:, 3] - rects[:, 1]),
                 depth_keys=_arr(geom, lay.depth_keys, np.uint32, P),
-                sorted_ids=_arr(geom, lay.sorted_ids, np.uint32, P))
+                sorted_ids=_arr(geom, lay.sorted_ids, np.uint32, 2 * P).view(P, 2)[:, 1].contiguous())
 
 
 def decode_img(img, W, H):
