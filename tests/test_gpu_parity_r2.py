@@ -184,8 +184,11 @@ def test_native_pose_depth_silhouette_vs_reference_two_calls(dgr, ref):
 
 def test_camera_gradients_clamped_scene(dgr):
     """Row a17 at the north_star bar: dL/d{viewmatrix, projmatrix, campos} within 1e-4 of fp64 autograd through the
-    oracle on 30k Gaussians whose opacities DO reach the 0.99 alpha clamp (the oracle differentiates the clamp the way
-    the reference's backward does: value clamped, gradient straight through)."""
+    oracle on 30k Gaussians whose opacities DO reach the 0.99 alpha clamp and some of which hit the x/z, y/z frustum
+    clamp of the EWA Jacobian (the oracle differentiates both clamps the way the reference's backward does — alpha:
+    value clamped, gradient straight through; frustum: clamped t.x / t.y held constant — which
+    tests/test_oracle_cpu.py::test_reference_gradient_conventions_under_both_clamps pins against the analytic
+    restatement of the reference, so the camera gradients are the ones consistent with its dL/dmeans3D)."""
     import gsr_synth as S
     from oracle import gs_oracle as O
     from tests.util import rel_err

@@ -35,6 +35,38 @@ def test_analytic_backward_matches_autograd_fp64():
         assert float((a - b).abs().max() / b.abs().max()) < 1e-6, name
 
 
+def test_reference_gradient_conventions_under_both_clamps():
+    """Where the reference's hand-written backward is NOT the true derivative — alpha clamped at 0.99 (gradient flows
+    straight through, CR/backward.cu:489-490) and x/z, y/z clamped at 1.3 tanfov (clamped t.x / t.y held constant,
+    CR/backward.cu:166-167,259-264) — differentiable_render(clamp_straight_through=True) follows the reference's
+    convention, so autograd through it equals the analytic restatement on a scene that hits both clamps.  This is
+    what makes it a valid oracle for the camera gradients (row a17), which the reference itself does not produce."""
+    P, W, H, deg = 4000, 96, 64, 1
+    gs, _, dL, _ = S.make_scene(P, W, H, seed=13, sh_degree=deg)
+    gs["opacities"] = torch.clamp(gs["opacities"] * 1.6, max=1.0)
+    cam = S.orbit_cameras(W, H, 3, (0.0, 0.0, 4.0), 0.5)[2]
+    bg, dt = torch.tensor([0.2, 0.5, 0.7]), torch.float64
+    leaf = {k: v.to(dt).clone().requires_grad_(True) for k, v in gs.items()}
+    img = O.differentiable_render(leaf["means3D"], leaf["opacities"], leaf["scales"], leaf["rotations"], leaf["shs"],
+                                  deg, cam.viewmatrix, cam.projmatrix, cam.campos, bg, W, H, cam.tanfovx, cam.tanfovy,
+                                  clamp_straight_through=True)
+    (img * dL.to(dt)).sum().backward()
+    pre, binning, fwd = O.rasterize_forward(gs["means3D"], gs["opacities"], cam.viewmatrix, cam.projmatrix, cam.campos,
+                                            bg, W, H, cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0,
+                                            None, gs["shs"], deg, dtype=dt)
+    g = O.rasterize_backward(dL, pre, binning, fwd, gs["means3D"], cam.viewmatrix, cam.projmatrix, cam.campos, bg, W,
+                             H, cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], deg,
+                             dtype=dt)
+    cp = O._cov2d_parts(gs["means3D"].to(dt), O.cov3d_from_scale_rot(gs["scales"].to(dt), 1.0, gs["rotations"].to(dt)),
+                        cam.viewmatrix.to(dt).reshape(16), W, H, cam.tanfovx, cam.tanfovy)
+    vis = pre["radii"] > 0
+    assert int(((cp["txtz"].abs() > cp["limx"]) | (cp["tytz"].abs() > cp["limy"]))[vis].sum()) > 0   # frustum clamp hit
+    for name, key in (("means3D", "dL_dmeans3D"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                      ("opacities", "dL_dopacity"), ("shs", "dL_dsh")):
+        a, b = g[key], leaf[name].grad
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-6, name
+
+
 def test_fp32_oracle_close_to_fp64():
     W, H, deg = 64, 48, 1
     gs, cam, dL, bg = _scene(400, W, H, deg, seed=8)
