@@ -58,7 +58,17 @@ def parse():
     ap.add_argument("--sh-degree", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip m1/m2/m3/iteration_ops/parity (scaling sweeps)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed blocks of --steps steps; the line reports the median")
+    ap.add_argument("--config", default="cmain", choices=["cmain", "c5", "custom"],
+                    help="cmain: 1M / 640x480 / K=8 (the metric's configuration); c5: BASELINE config 5, 5M / 1920x1080 / "
+                         "K=32; custom: take --P --W --H --keyframes as given")
+    a = ap.parse_args()
+    if a.config == "c5":
+        a.P, a.W, a.H, a.keyframes = 5_000_000, 1920, 1080, 32
+    elif (a.P, a.W, a.H, a.keyframes) != (1_000_000, 640, 480, 8):
+        a.config = "custom"
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,6 +239,105 @@ def measure_m2(rasterize, settings_cls, params, dL, device, args, fused=None, it
         out[name + "_fps"] = iters / (e0.elapsed_time(e1) / 1e3)
     out["what"] = "full SLAM render (pose transform + RGB + depth/silhouette) fwd+bwd, 1 GPU, same scene"
     return out
+
+
+def measure_m1(dgr, params, rs, dL, device, iters=50, warm=10):
+    """M1 as SURVEY.md §8(d) states it: ONE rasterizer call forward + backward through the stock API — one stream, no
+    prepare_forward, no grad_targets — median of `iters` CUDA-event-timed iterations after `warm` warm-ups.  `synced`
+    adds a host synchronisation after every backward, which is what a tracker iteration that reads its loss does
+    (R/slam/tracker.py:99-167)."""
+    P = params["means3D"].shape[0]
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+
+    def call():
+        m2 = torch.zeros(P, 3, device=device, requires_grad=True)
+        color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"], shs=p["shs"],
+                                              scales=p["scales"], rotations=p["rotations"])
+        color.backward(dL)
+        for t in p.values():
+            t.grad = None
+
+    out = {}
+    for name, sync in (("fps", False), ("synced_fps", True)):
+        for _ in range(warm):
+            call()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+        evs[0].record()
+        for i in range(iters):
+            call()
+            evs[i + 1].record()
+            if sync:
+                evs[i + 1].synchronize()
+        torch.cuda.synchronize()
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
+        out["m1_single_call_" + name] = 1e3 / per[len(per) // 2]
+        out["ms_" + name.replace("_fps", "").replace("fps", "median")] = per[len(per) // 2]
+    out["what"] = ("one GaussianRasterizer forward + backward of keyframe 0, stock API, one stream, median of "
+                   f"{iters} event-timed calls; synced = host waits for every call like a tracker iteration")
+    return out
+
+
+def measure_blend(dgr, params, rs, stages, device):
+    """(pixel, Gaussian) pairs/s of the two blend kernels and the contributing fraction, keyframe 0.
+    Counts come from gsr_blend_stats (a plain per-pixel replay of the finished forward)."""
+    lib = dgr._lib
+    lib.gsr_blend_stats.restype = ctypes.c_int
+    lib.gsr_blend_stats.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    P = params["means3D"].shape[0]
+    with torch.no_grad():
+        R, _, _, geom, binning, img = dgr._forward_native(params["means3D"], params["shs"], None, params["opacities"],
+                                                          params["scales"], params["rotations"], None, rs, rs.viewmatrix,
+                                                          rs.projmatrix, rs.campos, rs.bg)
+    out = torch.zeros(4, dtype=torch.int64, device=device)
+    rc = lib.gsr_blend_stats(torch.cuda.current_stream().cuda_stream, P, int(rs.image_width), int(rs.image_height),
+                             int(R.cap), geom.data_ptr(), binning.data_ptr(), img.data_ptr(), out.data_ptr())
+    if rc != 0:
+        raise RuntimeError(lib.gsr_last_error().decode())
+    upper, walked, blended, bwd_pairs = (int(x) for x in out.tolist())
+    d = {"pairs_upper_bound": upper, "pairs_walk_to_last_contributor": walked, "pairs_contributing": blended,
+         "pairs_evaluated_bwd": bwd_pairs, "contributing_fraction_of_upper_bound": blended / max(upper, 1),
+         "contributing_fraction_of_evaluated_bwd": blended / max(bwd_pairs, 1)}
+    if "render_fwd" in stages:
+        d["fwd_contributing_gpairs_per_s"] = blended / (stages["render_fwd"]["ms"] * 1e-3) / 1e9
+        d["fwd_upper_bound_gpairs_per_s"] = upper / (stages["render_fwd"]["ms"] * 1e-3) / 1e9
+    if "render_bwd" in stages:
+        d["bwd_contributing_gpairs_per_s"] = blended / (stages["render_bwd"]["ms"] * 1e-3) / 1e9
+        d["bwd_evaluated_gpairs_per_s"] = bwd_pairs / (stages["render_bwd"]["ms"] * 1e-3) / 1e9
+    d["what"] = ("keyframe 0: upper bound = sum over tiles of 256 x list length (SURVEY 8d); contributing = (pixel, splat) "
+                 "pairs actually blended; evaluated_bwd = 32 x (warp, entry) pairs the backward visits")
+    return d
+
+
+def parity_check(dgr, params, rs, dL, device):
+    """Once, outside every timed region: image and gradients of keyframe 0 against the unmodified compiled reference
+    (oracle/_ref) on the same inputs, max-norm relative error; the bench refuses to report a number otherwise."""
+    from oracle import ref_api
+    if not ref_api.available():
+        return {"checked": False, "why": "oracle/_ref/ref_dgr_C.so not present"}
+    P = params["means3D"].shape[0]
+    res = []
+    for fn in ("ours", "ref"):
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        m2 = torch.zeros(P, 3, device=device, requires_grad=True)
+        if fn == "ours":
+            color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"], shs=p["shs"],
+                                                  scales=p["scales"], rotations=p["rotations"])
+        else:
+            color, _ = ref_api.rasterize(p["means3D"], m2, p["opacities"], rs, shs=p["shs"], scales=p["scales"],
+                                         rotations=p["rotations"])
+        color.backward(dL)
+        res.append((color.detach(), {k: v.grad for k, v in p.items()}))
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+    errs = {"color": rel(res[0][0], res[1][0])}
+    errs.update({"d_" + k: rel(res[0][1][k], res[1][1][k]) for k in res[0][1]})
+    ok = all(e < 1e-4 for e in errs.values())
+    return {"checked": True, "ok": ok, "tolerance": 1e-4, "max_rel_err": {k: float(f"{v:.3g}") for k, v in errs.items()},
+            "against": "oracle/_ref (unmodified reference compiled for sm_100a), keyframe 0 of the timed workload"}
 
 
 def ssim_window(device):
@@ -479,37 +588,46 @@ def main():
         step()
     barrier()
     n0 = launch_count() if launch_count else 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    # `repeats` timed blocks of EXACTLY --steps steps, each bracketed by barrier + synchronize on both sides and timed
+    # with CUDA events on the launching stream; a block's time is the max over ranks, the line reports the median block.
+    block_ms = []
+    for _ in range(max(1, args.repeats)):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+        block_ms.append(ev0.elapsed_time(ev1))
     n1 = launch_count() if launch_count else 0
     if distributed and args.impl == "b200":
-        t = torch.tensor([ms], device=device)
+        t = torch.tensor(block_ms, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if ms < 400.0:   # short timed region: keep the same load going (untimed, same count on every rank) until the
-        for _ in range(min(400, int(400.0 / max(ms / args.steps, 1e-3)) + 1)):   # 100 ms sampler has a few samples
+        block_ms = [float(x) for x in t.tolist()]
+    ms = statistics.median(block_ms)
+    if sum(block_ms) < 400.0:   # short timed region: keep the same load going (untimed, same count on every rank) until
+        for _ in range(min(400, int(400.0 / max(ms / args.steps, 1e-3)) + 1)):   # the 100 ms sampler has a few samples
             step()
         barrier()
     clocks = sampler.stop() if rank == 0 else None
     frames = args.keyframes * args.steps
     value = frames / (ms / 1e3)
 
+    workloads = {"cmain": "C-main: 1M-Gaussian synthetic scene, 640x480, SH degree 0, 8 orbit keyframes/step",
+                 "c5": "C5 (BASELINE config 5): 5M-Gaussian synthetic scene, 1920x1080, SH degree 0, 32 orbit keyframes/step",
+                 "custom": "custom"}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C-main: 1M-Gaussian synthetic scene, 640x480, SH degree 0, 8 orbit keyframes/step"
-                   if (args.P, args.W, args.H, args.keyframes) == (1_000_000, 640, 480, 8) else "custom",
-                   "P": args.P, "W": args.W, "H": args.H, "keyframes_per_step": args.keyframes,
-                   "sh_degree": args.sh_degree, "parallelism": f"keyframe-sharded dp{world}" if args.impl == "b200" else "1 gpu",
-                   "streams_per_rank": int(os.environ.get("GSR_BENCH_STREAMS", "4")) if args.impl == "b200" else 1,
+        # identical in both arms (the driver compares it): only what defines the workload
+        "config": {"workload": workloads[args.config], "P": args.P, "W": args.W, "H": args.H,
+                   "keyframes_per_step": args.keyframes, "sh_degree": args.sh_degree,
                    "l2": "per-step working set (56 B/G params + 116 B/G grads + per-frame 48 B/G records and "
                          "24+ B/instance binning, > 400 MB) exceeds the 126 MB L2; no explicit flush"},
+        "run": {"parallelism": f"keyframe-sharded dp{world}" if args.impl == "b200" else "1 gpu (the reference has no multi-GPU path)",
+                "streams_per_rank": int(os.environ.get("GSR_BENCH_STREAMS", "4")) if args.impl == "b200" else 1,
+                "repeats": len(block_ms), "block_ms": [round(x, 3) for x in block_ms], "statistic": "median block"},
         "clocks": clocks,
     }
     if args.impl == "reference":
@@ -531,9 +649,26 @@ def main():
         print(json.dumps(line), flush=True)
         return 0
 
-    line["gpu_launches"] = int(n1 - n0)
-    line["config"]["R_mean"] = sum(R_list) / max(len(R_list), 1)
-    line["config"]["visible_mean"] = sum(vis_list) / max(len(vis_list), 1)
+    line["gpu_launches"] = int(n1 - n0) // max(1, len(block_ms))      # per timed block of --steps steps
+    line["run"]["R_mean"] = sum(R_list) / max(len(R_list), 1)
+    line["run"]["visible_mean"] = sum(vis_list) / max(len(vis_list), 1)
+
+    # ---- where a step's time goes on a rank: kernels vs the gradient exchange (CUDA events inside the step) ----
+    stepper.timing = True
+    tk, tc = [], []
+    for _ in range(5):
+        step()
+        tm = stepper.timings()
+        tk.append(tm["kernel_ms"])
+        tc.append(tm["comm_ms"])
+        barrier()
+    stepper.timing = False
+    t = torch.tensor([statistics.median(tk), statistics.median(tc)], device=device)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    line["kernel_ms"], line["comm_ms"] = round(float(t[0]), 4), round(float(t[1]), 4)
+    line["run"]["timing_note"] = ("kernel_ms: step start -> local gradient bucket complete; comm_ms: the exchange after it "
+                                  "(exposed part of the all-reduce); medians of 5 steps, max over ranks")
 
     # ---- per-stage profile (untimed pass with the library's stage events on) --------------------
     lib = dgr._lib
@@ -576,6 +711,19 @@ def main():
                         "alg_bytes_per_launch": stages[dom]["alg_bytes"], "ms_per_launch": stages[dom]["ms"],
                         "call_alg_bytes": sum(sb.values()), "call_ms_sum_of_stages": total_ms,
                         "call_frac": sum(sb.values()) / (total_ms * 1e-3) / 1e9 / peak}
+
+    if rank == 0 and not args.no_extras:
+        try:
+            line["blend"] = measure_blend(dgr, params, kfs[0], stages, device)
+        except Exception as ex:
+            line["blend"] = {"error": repr(ex)}
+        line["parity_check"] = parity_check(dgr, params, kfs[0], dL, device)
+        if line["parity_check"].get("checked") and not line["parity_check"]["ok"]:
+            print(json.dumps({"error": "parity check against oracle/_ref failed", "parity_check": line["parity_check"]}),
+                  flush=True)
+            return 1
+    if distributed:
+        dist.barrier()
 
     # ---- end to end through the public API with HOST buffers ------------------------------------
     if not args.no_e2e:
@@ -666,14 +814,20 @@ def main():
                                "copies run on a copy stream with double-buffered device parameters / result staging so "
                                "they overlap the neighbouring steps' kernels"}
 
-    if rank == 0 and world == 1:
+    extras = rank == 0 and world == 1 and not args.no_extras
+    if extras:
+        try:
+            line["m1"] = measure_m1(dgr, params, kfs[0], dL, device)
+        except Exception as ex:
+            line["m1"] = {"error": repr(ex)}
+    if extras:
         try:
             line["m2"] = measure_m2(
                 lambda m3, m2, op, rs_, **kw: dgr.GaussianRasterizer(rs_)(means3D=m3, means2D=m2, opacities=op, **kw),
                 dgr.GaussianRasterizationSettings, params, dL, device, args, fused=dgr.GaussianRasterizer)
         except Exception as ex:
             line["m2"] = {"error": repr(ex)}
-    if rank == 0 and world == 1:
+    if extras:
         try:
             line["m3"] = measure_m3("b200", dgr.GaussianRasterizer, dgr.GaussianRasterizationSettings, params, device, args)
         except Exception as ex:

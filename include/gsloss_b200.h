@@ -92,6 +92,27 @@ int gsr_adam_step(gsr_stream_t stream, float* params, float* grads, float* exp_a
                   int32_t num_segments, const int64_t* seg_end, const double* seg_lr, double beta1, double beta2, double eps,
                   int64_t step, float grad_scale, int32_t zero_grads);
 
+/* Map surgery over the flat parameter / optimizer buffers: the reference's _prune_optimizer and
+ * cat_tensors_to_optimizer (R/slam/gaussian_model.py:380-399, :418-451; called from prune_points :401-416 and
+ * densification_postfix :453-485).  A flat buffer is ngroups slabs [P, widths[g]] fp32 one after the other (the
+ * optimizer-group order); the parameters and both Adam moments are nbuf parallel buffers with that layout.
+ *
+ * gsr_compact_scan:   new_index[i] = number of rows j < i with keep[j] != 0 (keep == NULL keeps every row);
+ *                     *count (device) = number of kept rows.  ws: gsr_compact_ws_bytes(P) of device scratch.
+ * gsr_compact_gather: for every kept row i, every group g and every buffer b:
+ *                     dst[b][group g of a rows_out-row layout][new_index[i]][:] = src[b][group g of a P-row layout][i][:].
+ *                     rows_out >= kept rows; rows past the kept ones (the ones an extension appends) are left untouched.
+ *                     With keep == NULL and new_index == NULL it re-lays the P rows out for rows_out rows (extension).
+ * Exact copies: the result equals torch's boolean-mask indexing / torch.cat bit for bit. */
+#define GSR_COMPACT_MAX_GROUPS 16
+#define GSR_COMPACT_MAX_BUFFERS 4
+size_t gsr_compact_ws_bytes(int64_t P);
+int gsr_compact_scan(gsr_stream_t stream, int64_t P, const uint8_t* keep, uint32_t* new_index, int64_t* count, void* ws,
+                     size_t ws_bytes);
+int gsr_compact_gather(gsr_stream_t stream, int64_t P, int64_t rows_out, int32_t ngroups, const int32_t* widths,
+                       const uint8_t* keep, const uint32_t* new_index, int32_t nbuf, const float* const* src,
+                       float* const* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 4
+#define GSR_ABI_VERSION 5
 
 typedef void* gsr_stream_t; /* cudaStream_t */
 
@@ -161,6 +161,15 @@ int gsr_backward(gsr_stream_t stream, const gsr_gaussians* g, const gsr_camera* 
 /* present[i] = 1 if Gaussian i passes the near-plane test (z_view > 0.1). */
 int gsr_mark_visible(gsr_stream_t stream, int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present);
+
+/* Diagnostic (bench / tests; not on the hot path): work counts of the blend stage of a FINISHED forward, from a plain
+ * per-pixel replay of the tile lists (SURVEY.md §8d asks for (pixel, Gaussian) pairs/s and the contributing fraction).
+ * out (device, 4 x uint64): [0] sum over tiles of 256 * list length — the pairs before early termination;
+ * [1] sum over pixels of the position of the last contributor — pairs a per-pixel walk evaluates (the reference's
+ * forward, CR/forward.cu:306-357, walks at least these); [2] pairs actually blended (alpha >= 1/255, power <= 0);
+ * [3] 32 x the (warp, list entry) pairs the forward recorded — the pairs this library's backward evaluates. */
+int gsr_blend_stats(gsr_stream_t stream, int32_t P, int32_t width, int32_t height, int64_t R, const void* geom_ws,
+                    const void* binning_ws, const void* img_ws, uint64_t* out);
 
 /* Optional stage profiler (off by default).  When enabled, every stage boundary records a CUDA
  * event on the caller's stream; gsr_profile_collect() synchronises, sums the elapsed time per stage

@@ -355,14 +355,51 @@ __device__ __forceinline__ void load_rect(const uint2* __restrict__ perm, const 
     }
 }
 
+// Exclusive scan of the per-tile totals -> ranges[t] = {start, end}, starts[t].  One CTA of 1024 threads, any T.
+// (A heaviest-tiles-first launch order for the blend kernels was tried here and measured no gain on scenes whose
+// tiles carry similar loads; the blend kernels take tiles in index order.)
+__device__ __forceinline__ void cta_tile_starts(const uint32_t* totals, int T, uint2* __restrict__ ranges,
+                                                uint32_t* __restrict__ starts, uint32_t* s_warp, uint32_t* s_carry)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) *s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += 1024) {
+        const int t = t0 + tid;
+        const uint32_t v = (t < T) ? __ldcg(totals + t) : 0u;   // written by other CTAs of this launch
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t x = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += s_warp[w];
+        const uint32_t carry = *s_carry;
+        const uint32_t start = carry + wb + incl - v;
+        if (t < T) {
+            starts[t] = start;
+            ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
+        }
+        __syncthreads();
+        if (tid == 1023) *s_carry = carry + wb + incl;
+        __syncthreads();
+    }
+}
+
 // Column scan of H[chunks][bins]: in place H[c][b] <- sum_{c' < c} H[c'][b]; totals[b] <- sum_c H[c][b].
-// One CTA per 32 bins; the chunk axis is split into 32 segments handled by the 32 warps.
+// One CTA per 32 bins; the chunk axis is split into 32 segments handled by the 32 warps.  The CTA that finishes last
+// (ticket counter) turns the totals into the tile ranges, so the partition needs no separate launch for that.
 constexpr int kScanSegs = 32;
 __global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
-                                                                uint32_t* __restrict__ totals,
-                                                                const uint32_t* __restrict__ counters, uint32_t cap)
+                                                                uint32_t* __restrict__ totals, uint2* __restrict__ ranges,
+                                                                uint32_t* __restrict__ starts,
+                                                                uint32_t* __restrict__ counters, uint32_t cap)
 {
     __shared__ uint32_t s_seg[kScanSegs][32];
+    __shared__ uint32_t s_carry, s_last;
     if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
@@ -384,33 +421,105 @@ __global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __rest
         }
         if (seg == kScanSegs - 1) totals[b] = run;
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[kCntScanDone], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        cta_tile_starts(totals, bins, ranges, starts, &s_seg[0][0], &s_carry);
+    }
+}
+
+// Rank of this lane's instance among the instances of the same tile this warp has seen so far, and count it.
+// `cnt` / `tag`: the warp's private per-tile counters (16 bit) and scratch bytes in shared memory.  The instances
+// of a step come from a handful of neighbouring splats and a splat's tiles are distinct, so two lanes rarely
+// hold the same tile: every lane writes its lane id to tag[tile] and reads it back — if nobody lost that race all
+// tiles are distinct and the rank is a plain (non-atomic) read-increment-write; only otherwise are same-tile lanes
+// matched (one ballot per tile-id bit) and ranked in lane order.  No shared-memory atomics (2 cycles per lane).
+__device__ __forceinline__ uint32_t warp_rank_tile(uint16_t* cnt, uint8_t* tag, uint32_t tile, bool valid, int tbits)
+{
+    const int lane = threadIdx.x & 31;
+    if (valid) tag[tile] = (uint8_t)lane;
+    __syncwarp();
+    const bool lost = valid && tag[tile] != (uint8_t)lane;
+    const uint32_t old = valid ? cnt[tile] : 0u;
+    uint32_t rank = old;
+    if (!__any_sync(kFullMask, lost)) {
+        if (valid) cnt[tile] = (uint16_t)(old + 1u);
+    } else {
+        const unsigned peers = match_any_bits(tile, valid, tbits);
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) cnt[tile] = (uint16_t)(old + __popc(peers));
+        rank = old + __popc(peers & lanemask_lt());
+    }
+    __syncwarp();
+    return rank;
 }
 
 // Pass A.  A CTA owns a contiguous chunk of depth-ordered Gaussians.  It loads their tile rectangles,
 // scans the instance counts in shared memory and gives every warp an EQUAL share of the chunk's
 // instances (a share may start and end in the middle of a splat — a splat's tiles are distinct, so any
 // cut keeps the per-tile order intact).  Splats covering hundreds of tiles would otherwise serialise
-// the one warp that owns them.  Each warp then (1) claims a contiguous segment of the instance stream
-// with one atomicAdd (segments may sit anywhere in the stream; only their contents are ordered),
-// (2) enumerates its instances ONCE, writing {tile, Gaussian id} records with coalesced 8-byte stores,
-// and (3) adds them to the CTA's tile histogram (row c of H).
-// Dynamic shared memory: uint32 s_hist[T], s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1].
-__global__ void __launch_bounds__(1024) k_tile_count(const uint2* __restrict__ perm, int per_cta,
-                                                    const ushort4* __restrict__ rects, int gx, int T,
-                                                    uint32_t* __restrict__ hist, uint2* __restrict__ stream,
-                                                    uint2* __restrict__ segs, uint32_t* __restrict__ counters, uint32_t cap)
+// the one warp that owns them.  Each warp enumerates its share twice:
+//   phase 1 counts its instances per tile (private 16-bit counters for all T tiles in shared memory — what the
+//           B200's 227 KB buys); then, per tile, the counts are prefixed over the CTA's warps and their sum
+//           becomes row c of the histogram matrix H;
+//   phase 2 ranks every instance among the CTA's earlier instances of the same tile (prefix + running count) and
+//           writes one {tile | rank << 16, Gaussian id} record into a segment of the instance stream claimed with
+//           one atomicAdd (segments may sit anywhere in the stream; only their contents are ordered).
+// Nothing is read back: pass B only adds the two global prefixes.
+// Dynamic shared memory: uint32 s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1]; uint16 s_cnt[nwarps][T];
+// uint8 s_tag[nwarps][T].
+template <typename F>
+__device__ __forceinline__ void warp_share_for_each(const uint32_t* s_id, const uint32_t* s_pk, const uint32_t* s_ex,
+                                                    int per_cta, int first, uint32_t a, uint32_t b, int gx, F&& f)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t done = 0;
+    for (int g0 = first; g0 < per_cta && s_ex[g0] < b; g0 += 32) {
+        const int g = g0 + lane;
+        uint32_t id = 0, packed = 1u << 20, kb = 0, cnt = 0;
+        if (g < per_cta) {
+            const uint32_t ex = s_ex[g], full = s_ex[g + 1] - ex;
+            if (ex < b && full != 0) {
+                kb = a > ex ? a - ex : 0u;
+                const uint32_t ke = min(full, b - ex);
+                cnt = ke - kb;
+                id = s_id[g];
+                packed = s_pk[g];
+            }
+        }
+        const uint32_t round_total = __reduce_add_sync(kFullMask, cnt);
+        warp_for_each_instance(packed, kb, cnt, gx, [&](uint32_t tile, int src, bool valid, uint32_t i) {
+            f(tile, __shfl_sync(kFullMask, id, src), valid, done + i);
+        });
+        done += round_total;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_tile_rank(const uint2* __restrict__ perm, int per_cta,
+                                                   const ushort4* __restrict__ rects, int gx, int T,
+                                                   uint32_t* __restrict__ hist, uint2* __restrict__ stream,
+                                                   uint2* __restrict__ segs, uint32_t* __restrict__ counters, uint32_t cap)
 {
     if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
     const int n = (int)counters[kCntVisible];          // the depth sort kept only the visible Gaussians
     uint32_t* claim = counters + kCntClaim;
     extern __shared__ uint32_t s_dyn[];
-    uint32_t* s_hist = s_dyn;
-    uint32_t* s_id = s_dyn + T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    uint32_t* s_id = s_dyn;
     uint32_t* s_pk = s_id + per_cta;
     uint32_t* s_ex = s_pk + per_cta;       // [per_cta + 1] exclusive instance offsets inside the chunk
+    const int Tp = (T + 7) & ~7;           // row pitch: keeps every row 16-byte aligned
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_ex + ((per_cta + 1 + 3) & ~3));
+    uint8_t* s_tag = reinterpret_cast<uint8_t*>(s_cnt + (size_t)nwarps * Tp);
     __shared__ uint32_t s_wsum[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int t = tid; t < T; t += blockDim.x) s_hist[t] = 0;
+    {   // zero the counters (the tags need no initial value)
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+        const int n16 = nwarps * Tp / 8;
+        for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     const int c0 = blockIdx.x * per_cta;
     const int m = min(per_cta, n - c0);    // Gaussians in this chunk
     // load + block-wide exclusive scan of the counts (thread t owns the contiguous slice [t*q, (t+1)*q))
@@ -455,6 +564,7 @@ __global__ void __launch_bounds__(1024) k_tile_count(const uint2* __restrict__ p
         segs[(size_t)blockIdx.x * nwarps + warp] = make_uint2(seg, len);
     }
     seg = __shfl_sync(kFullMask, seg, 0);
+    int first = 0;
     if (len != 0) {
         // first splat of the share: last g with s_ex[g] <= a  (s_ex is non-decreasing; zero-count splats only at the end)
         int lo = 0, hi = per_cta;          // invariant: s_ex[lo] <= a < s_ex[hi]
@@ -462,196 +572,98 @@ __global__ void __launch_bounds__(1024) k_tile_count(const uint2* __restrict__ p
             const int mid = (lo + hi) >> 1;
             if (s_ex[mid] <= a) lo = mid; else hi = mid;
         }
-        uint32_t done = 0;
-        for (int g0 = lo; g0 < per_cta && s_ex[g0] < b; g0 += 32) {
-            const int g = g0 + lane;
-            uint32_t id = 0, packed = 1u << 20, kb = 0, cnt = 0;
-            if (g < per_cta) {
-                const uint32_t ex = s_ex[g], full = s_ex[g + 1] - ex;
-                if (ex < b && full != 0) {
-                    kb = a > ex ? a - ex : 0u;
-                    const uint32_t ke = min(full, b - ex);
-                    cnt = ke - kb;
-                    id = s_id[g];
-                    packed = s_pk[g];
-                }
-            }
-            const uint32_t round_total = __reduce_add_sync(kFullMask, cnt);
-            warp_for_each_instance(packed, kb, cnt, gx, [&](uint32_t tile, int src, bool valid, uint32_t i) {
-                const uint32_t gid = __shfl_sync(kFullMask, id, src);
-                if (valid) {
-                    stream[(size_t)seg + done + i] = make_uint2(tile, gid);
-                    atomicAdd(&s_hist[tile], 1u);
-                }
-            });
-            done += round_total;
-        }
+        first = lo;
     }
+    uint16_t* my = s_cnt + (size_t)warp * Tp;
+    uint8_t* my_tag = s_tag + (size_t)warp * Tp;
+    int tbits = 1;
+    while ((1 << tbits) < T) tbits++;
+    if (len != 0)
+        warp_share_for_each(s_id, s_pk, s_ex, per_cta, first, a, b, gx, [&](uint32_t tile, uint32_t, bool valid, uint32_t) {
+            warp_rank_tile(my, my_tag, tile, valid, tbits);
+        });
     __syncthreads();
     uint32_t* row = hist + (size_t)blockIdx.x * T;
-    for (int t = tid; t < T; t += blockDim.x) row[t] = s_hist[t];
-}
-
-// Exclusive scan of the per-tile totals -> ranges[t] = {start, end}.  Single CTA, any T.
-// (A heaviest-tiles-first launch order for the blend kernels was tried here and measured no gain on scenes whose
-// tiles carry similar loads; the blend kernels take tiles in index order.)
-__global__ void __launch_bounds__(1024) k_tile_starts(const uint32_t* __restrict__ totals, int T, uint2* __restrict__ ranges,
-                                                      uint32_t* __restrict__ starts, const uint32_t* __restrict__ counters,
-                                                      uint32_t cap)
-{
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (counters[kCntR] > cap) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    for (int t = tid; t < T; t += blockDim.x) {     // per tile: exclusive prefix over the warps, total -> H[c][t]
+        uint32_t acc = 0;
+#pragma unroll 8
+        for (int w = 0; w < nwarps; w++) {
+            const uint32_t c = s_cnt[(size_t)w * Tp + t];
+            s_cnt[(size_t)w * Tp + t] = (uint16_t)acc;
+            acc += c;
+        }
+        row[t] = acc;
+    }
     __syncthreads();
-    for (int t0 = 0; t0 < T; t0 += 1024) {
-        const int t = t0 + tid;
-        const uint32_t v = (t < T) ? totals[t] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t x = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= o) incl += x;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t wb = 0;
-        for (int w = 0; w < warp; w++) wb += s_warp[w];
-        const uint32_t carry = s_carry;
-        const uint32_t start = carry + wb + incl - v;
-        if (t < T) {
-            starts[t] = start;
-            ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
-        }
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + wb + incl;
-        __syncthreads();
+    if (len != 0) {
+        uint2* out = stream + seg;
+        warp_share_for_each(s_id, s_pk, s_ex, per_cta, first, a, b, gx, [&](uint32_t tile, uint32_t gid, bool valid, uint32_t i) {
+            const uint32_t rank = warp_rank_tile(my, my_tag, tile, valid, tbits);
+            if (valid) out[i] = make_uint2(tile | (rank << 16), gid);
+        });
     }
 }
 
-// Lanes holding the same tile id.  Ballot-per-bit: tile ids need few bits and neighbouring instances repeat
-// them, where the hardware MATCH (used for the random depth digits above) measured slower.
-__device__ __forceinline__ unsigned tile_peers(uint32_t tile, bool valid, int tbits)
-{
-    return match_any_bits(tile, valid, tbits);
-}
-
-// Pass B.  Same CTA / warp <-> Gaussian-range mapping as pass A; no enumeration any more: each warp
-// streams its segment twice with coalesced 8-byte accesses.
-//   sweep 1: rank every instance inside the warp's range for its tile (per-warp 16-bit counters,
-//            same-tile lanes of a step ranked in lane order) and store the rank back into the record;
-//   prefix : per tile, exclusive prefix of the warp counts over the CTA's warps (+ CTA base + tile start);
-//   sweep 2: point_list[start[tile] + prefix[warp][tile] + rank] = Gaussian id.
-// Dynamic shared memory: uint32 s_start[T]; uint16 s_cnt[nwarps][T].
+// Pass B.  Same CTA / warp <-> segment mapping as pass A; every warp streams its segment once with coalesced
+// 8-byte loads (four steps in flight): point_list[start[tile] + H[c][tile] + rank] = Gaussian id.
+// Dynamic shared memory: uint32 s_start[T].
 __global__ void __launch_bounds__(1024) k_tile_scatter(int T, const uint32_t* __restrict__ base,
-                                                      const uint32_t* __restrict__ starts, uint2* __restrict__ stream,
+                                                      const uint32_t* __restrict__ starts, const uint2* __restrict__ stream,
                                                       const uint2* __restrict__ segs, uint32_t* __restrict__ point_list,
                                                       const uint32_t* __restrict__ counters, uint32_t cap)
 {
     extern __shared__ uint32_t s_dyn[];
     if (counters[kCntR] > cap) return;
     uint32_t* s_start = s_dyn;
-    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_dyn + T);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t* row = base + (size_t)blockIdx.x * T;
-    for (int t = tid; t < T; t += blockDim.x) s_start[t] = starts[t] + row[t];
-    {   // zero the counters with 128-bit stores (s_cnt starts 4*T bytes into the 16-byte aligned dynamic block)
-        const size_t bytes = (size_t)nwarps * T * 2;
-        char* p = reinterpret_cast<char*>(s_cnt);
-        const size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
-        for (size_t i = tid; i < head / 2 && i * 2 < bytes; i += blockDim.x) s_cnt[i] = 0;
-        const size_t body = bytes > head ? (bytes - head) / 16 : 0;
-        uint4* p4 = reinterpret_cast<uint4*>(p + head);
-        for (size_t i = tid; i < body; i += blockDim.x) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (size_t i = (head + body * 16) / 2 + tid; i < bytes / 2; i += blockDim.x) s_cnt[i] = 0;
-    }
-    __syncthreads();
     const uint2 seg = segs[(size_t)blockIdx.x * nwarps + warp];
-    uint2* my_stream = stream + seg.x;
+    for (int t = tid; t < T; t += blockDim.x) s_start[t] = starts[t] + row[t];
+    __syncthreads();
+    const uint2* my_stream = stream + seg.x;
     const uint32_t len = seg.y;
-    uint16_t* my = s_cnt + (size_t)warp * T;
-    int tbits = 1;
-    while ((1 << tbits) < T) tbits++;
-    // sweep 1 (records are loaded four steps ahead: the per-step work is a short dependent chain, so
-    // an un-prefetched L2 round trip per step would dominate the warps that own a very large splat)
-    for (uint32_t b0 = 0; b0 < len; b0 += 128) {
-        uint32_t tl[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t i = b0 + u * 32 + lane;
-            tl[u] = (i < len) ? my_stream[i].x : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t i = b0 + u * 32 + lane;
-            if (b0 + u * 32 >= len) break;
-            const bool valid = i < len;
-            const uint32_t tile = tl[u];
-            const unsigned peers = tile_peers(tile, valid, tbits);
-            const int leader = valid ? __ffs(peers) - 1 : lane;
-            uint32_t old = 0;
-            if (valid && lane == leader) {
-                old = my[tile];
-                my[tile] = (uint16_t)(old + __popc(peers));
-            }
-            old = __shfl_sync(kFullMask, old, leader);
-            if (valid) my_stream[i].x = tile | ((old + __popc(peers & lanemask_lt())) << 16);
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    for (int t = tid; t < T; t += blockDim.x) {
-        uint32_t run = 0;
-#pragma unroll 8
-        for (int w = 0; w < nwarps; w++) {
-            const uint32_t c = s_cnt[(size_t)w * T + t];
-            s_cnt[(size_t)w * T + t] = (uint16_t)run;
-            run += c;
-        }
-    }
-    __syncthreads();
-    // sweep 2
     for (uint32_t b0 = 0; b0 < len; b0 += 128) {
         uint2 r[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const uint32_t i = b0 + u * 32 + lane;
-            r[u] = (i < len) ? my_stream[i] : make_uint2(0u, 0u);
+            r[u] = (i < len) ? __ldcs(my_stream + i) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const uint32_t i = b0 + u * 32 + lane;
-            if (i < len) {
-                const uint32_t tile = r[u].x & 0xffffu, rank = r[u].x >> 16;
-                point_list[s_start[tile] + my[tile] + rank] = r[u].y;
-            }
+            if (i < len) point_list[s_start[r[u].x & 0xffffu] + (r[u].x >> 16)] = r[u].y;
         }
     }
 }
 
-// Chunking of the tile partition: per-warp counters are 16 bit, so a warp may own at most 65535
+// Chunking of the tile partition: ranks are 16 bit and relative to the CTA, so a CTA may own at most 65535
 // Gaussians; the CTA count is capped so that the H matrix stays small.
+static size_t tile_rank_smem(int T, int per_cta, int warps)
+{
+    const size_t Tp = (size_t)((T + 7) & ~7);
+    return (size_t)(2 * per_cta + ((per_cta + 1 + 3) & ~3)) * 4 + Tp * 3 * (size_t)warps;
+}
 void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem_count, size_t& smem_scatter)
 {
-    // as many warps per CTA as the 16-bit per-warp counters allow in 200 KB of shared memory, at most 32:
-    // the kernels are latency-bound walks, so short per-warp ranges matter more than anything else.
-    warps = 32;
-    while (warps > 1 && (size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024) warps >>= 1;
-    if ((size_t)T * (4 + 2 * (size_t)warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
+    // as many warps per CTA as their private per-tile counters (3 bytes per tile) allow in ~200 KB of shared memory
+    // next to the chunk's rectangles, at most 32: the kernel is a latency-bound walk, so short per-warp shares matter
+    // more than anything else.
     const int max_ctas = 4 * 148;   // (sizing to exactly one resident wave measured slower)
-    per_cta = 64 * (warps > 0 ? warps : 1);
-    if (per_cta < 1024) per_cta = 1024;
-    if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
-    per_cta = (per_cta + 31) / 32 * 32;
-    ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
-    // pass A also keeps id / packed rect / offset of every Gaussian of the chunk in shared memory
-    while ((size_t)T * 4 + (size_t)per_cta * 12 + 4 > 200 * 1024 && per_cta > 1024) {
-        per_cta = (per_cta / 2 + 31) / 32 * 32;
-        ctas = (P + per_cta - 1) / per_cta;
+    warps = 32;
+    for (;;) {
+        per_cta = 64 * warps;
+        if (per_cta < 1024) per_cta = 1024;
+        if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
+        per_cta = (per_cta + 31) / 32 * 32;
+        while (tile_rank_smem(T, per_cta, warps) > 200 * 1024 && per_cta > 1024) per_cta = (per_cta / 2 + 31) / 32 * 32;
+        if (tile_rank_smem(T, per_cta, warps) <= 200 * 1024 || warps == 1) break;
+        warps >>= 1;
     }
-    smem_count = (size_t)T * 4 + (size_t)per_cta * 12 + 4;
-    smem_scatter = (size_t)T * (4 + 2 * (size_t)(warps > 0 ? warps : 1));
+    if (tile_rank_smem(T, per_cta, warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
+    ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
+    smem_count = tile_rank_smem(T, per_cta, warps > 0 ? warps : 1);
+    smem_scatter = (size_t)T * 4;
 }
 
 // `cap`: number of instances the caller's stream / point_list arrays can hold.  If the scene has more (counters[kCntR],
@@ -668,13 +680,13 @@ int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {   // opt in to the large B200 carve-out once per device
-        cudaFuncSetAttribute(k_tile_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_tile_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         configured[dev] = true;
     }
-    k_tile_count<<<ctas, warps * 32, smem_c, s>>>(perm, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, counters, cap);
-    k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals, counters, cap);
-    k_tile_starts<<<1, 1024, 0, s>>>(w.tile_totals, T, ranges, w.tile_starts, counters, cap);
+    k_tile_rank<<<ctas, warps * 32, smem_c, s>>>(perm, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, counters, cap);
+    k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals, ranges, w.tile_starts,
+                                                           counters, cap);
     k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list, counters, cap);
     return 0;
 }

@@ -337,7 +337,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
                               bw.point_list, stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
-    GSR_MARK(ST_TILE_PARTITION, stream, 4);
+    GSR_MARK(ST_TILE_PARTITION, stream, 3);
     launch_render_fwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
                       out_color, bw.contrib, g->extra_mode == 1 ? gw.extra_gen : g->extra_colors, out_extra,
                       gw.counters, (uint32_t)R, stream);
@@ -395,6 +395,23 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     launch_preprocess_bwd(a, stream);
     GSR_STAGE("preprocess_backward", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS_BWD, stream, 1);
+    return GSR_OK;
+}
+
+int gsr_blend_stats(gsr_stream_t stream_, int32_t P, int32_t W, int32_t H, int64_t R, const void* geom_ws,
+                    const void* binning_ws, const void* img_ws, uint64_t* out)
+{
+    if (P <= 0 || W <= 0 || H <= 0 || R < 0) return fail(GSR_ERR_INVALID, "bad size");
+    if (!geom_ws || !img_ws || !out || (R > 0 && !binning_ws)) return fail(GSR_ERR_INVALID, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GeomWS gw = geom_ws_carve((char*)geom_ws, P, W, H);
+    ImgWS iw = img_ws_carve((char*)img_ws, W, H);
+    BinWS bw = bin_ws_carve((char*)binning_ws, R);
+    GSR_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(uint64_t), stream));
+    if (R == 0) return GSR_OK;
+    launch_blend_stats(W, H, (W + kTile - 1) / kTile, (H + kTile - 1) / kTile, iw.ranges, bw.point_list, gw.rec,
+                       iw.n_contrib, bw.contrib, reinterpret_cast<unsigned long long*>(out), stream);
+    GSR_STAGE("blend_stats", 0, stream);
     return GSR_OK;
 }
 

@@ -26,6 +26,7 @@ constexpr int kCntVisible = 2;   // number of visible Gaussians (= length of the
 constexpr int kCntTicket = 3;    // [4] block tickets of the four depth-sort passes (slots 3..6)
 constexpr int kCntChunkFwd = 8;  // chunk ticket of k_preprocess_fwd
 constexpr int kCntChunkBwd = 9;  // chunk ticket of k_preprocess_bwd (wraps to zero by itself)
+constexpr int kCntScanDone = 10; // CTAs of the tile partition's column scan that have finished
 constexpr int kSortDigits = 4;   // 8-bit digits of the depth sort
 constexpr int kSortBins = 256;
 
@@ -103,6 +104,9 @@ void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const 
                        const uint8_t* contrib, const float* dL_dpix, float* dL_dmean2D /*[P,3]*/, float* dL_dconic /*[P,4]*/,
                        float* dL_dopacity, float* dL_dcolors /*[P,3]*/, const float* extra, const float* dL_dpix_extra,
                        float* dL_dextra, cudaStream_t s);
+
+void launch_blend_stats(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list, const float4* rec,
+                        const uint32_t* n_contrib, const uint8_t* contrib, unsigned long long* out, cudaStream_t s);
 
 struct PreBwdArgs {
     int P, D, M, W, H;

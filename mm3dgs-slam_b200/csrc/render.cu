@@ -475,4 +475,57 @@ void launch_render_bwd(int W, int H, int gx, int gy, const uint2* ranges, const 
                                                     nullptr, nullptr);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Diagnostic: work counts of the blend stage of a finished forward (gsr_blend_stats; bench / tests only).
+// A plain per-pixel replay of the tile's list — no culling, no staging — so that the counts do not depend on
+// any of the shortcuts the product kernels take.
+//   out[0] += 256 * list length                     (pixel, splat) pairs before early termination
+//   out[1] += per pixel, entries up to its last contributor   (what a per-pixel walk has to evaluate)
+//   out[2] += per pixel, entries actually blended              (contributing pairs)
+//   out[3] += 32 * (warp, entry) pairs recorded by k_render_fwd (pairs the backward evaluates)
+__global__ void __launch_bounds__(256) k_blend_stats(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                     const uint32_t* __restrict__ point_list,
+                                                     const float4* __restrict__ rec, const uint32_t* __restrict__ n_contrib,
+                                                     const uint8_t* __restrict__ contrib, unsigned long long* out)
+{
+    const int tile = (int)blockIdx.x;
+    const TileGeom g = tile_geom(tile, gx, W, H);
+    const uint2 range = ranges[tile];
+    const uint32_t n = range.y - range.x;
+    unsigned long long walked = 0, blended = 0, visits = 0;
+    if (g.inside) {
+        const uint32_t last = n_contrib[g.py * W + g.px];
+        walked = last;
+        const float pixx = (float)g.px, pixy = (float)g.py;
+        for (uint32_t i = 0; i < last; i++) {
+            const float4* r = rec + (size_t)point_list[range.x + i] * 3;
+            const float4 a = r[0], co = r[1];
+            const float dx = a.x - pixx, dy = a.y - pixy;
+            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+            const float alpha = fminf(0.99f, co.w * expf(power));
+            if (!(power > 0.0f) && !(alpha < 1.0f / 255.0f)) blended++;
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += 256) visits += 32ull * (unsigned)__popc((unsigned)contrib[range.x + i]);
+    __shared__ unsigned long long s_acc[3];
+    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    atomicAdd(&s_acc[0], walked);
+    atomicAdd(&s_acc[1], blended);
+    atomicAdd(&s_acc[2], visits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(out + 0, 256ull * n);
+        atomicAdd(out + 1, s_acc[0]);
+        atomicAdd(out + 2, s_acc[1]);
+        atomicAdd(out + 3, s_acc[2]);
+    }
+}
+
+void launch_blend_stats(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list, const float4* rec,
+                        const uint32_t* n_contrib, const uint8_t* contrib, unsigned long long* out, cudaStream_t s)
+{
+    k_blend_stats<<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, n_contrib, contrib, out);
+}
+
 }  // namespace gsr

@@ -94,7 +94,7 @@ def _load():
                                  ctypes.POINTER(_Grads)]
     lib.gsr_mark_visible.restype = ctypes.c_int
     lib.gsr_mark_visible.argtypes = [vp, i32, vp, vp, vp, vp]
-    if lib.gsr_abi_version() != 4:
+    if lib.gsr_abi_version() != 5:
         raise ImportError("libgsrast_b200.so ABI version mismatch")
     return lib
 

@@ -142,6 +142,22 @@ class ShardedMapStep:
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
+        # optional per-step timing (CUDA events on the step's main stream): set .timing = True, read .timings()
+        self.timing = False
+        self._marks = None
+
+    def _mark(self, i):
+        if self.timing and self._marks is not None:
+            self._marks[i].record(torch.cuda.current_stream())
+
+    def timings(self):
+        """After a step run with .timing = True: dict(kernel_ms, comm_ms) of that step on this rank — kernel_ms from the
+        start of the step to the point where the local gradient bucket is complete, comm_ms the exchange after it."""
+        if self._marks is None:
+            return None
+        torch.cuda.synchronize()
+        m = self._marks
+        return {"kernel_ms": m[0].elapsed_time(m[1]), "comm_ms": m[1].elapsed_time(m[2])}
 
     def _targets(self, i, first=False):
         """Accumulators of stream i.  `first`: this is the first frame written into them in this step, so the
@@ -202,6 +218,11 @@ class ShardedMapStep:
 
     def _step(self, keyframes: Sequence):
         mine = self.my_keyframes(keyframes)
+        if self.timing and next(iter(self.params.values())).is_cuda:
+            self._marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        else:
+            self._marks = None
+        self._mark(0)
         if self.overwrite_first and self.forward_fn is not None and mine:
             self.bucket.views["opacities"].zero_()
         else:
@@ -228,6 +249,8 @@ class ShardedMapStep:
             losses = [o.detach() for o, _ in outs]
         else:
             losses = [self.frame_fn(self.params, kf) for kf in mine]
+        self._mark(1)
         if self.world > 1:
             dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self._mark(2)
         return losses

@@ -43,6 +43,13 @@ def _bind():
     _lib.gsr_adam_step.restype = ctypes.c_int
     _lib.gsr_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, ctypes.POINTER(i64), ctypes.POINTER(f64), f64, f64, f64,
                                    i64, f32, i32]
+    _lib.gsr_compact_ws_bytes.restype = sz
+    _lib.gsr_compact_ws_bytes.argtypes = [i64]
+    _lib.gsr_compact_scan.restype = ctypes.c_int
+    _lib.gsr_compact_scan.argtypes = [vp, i64, vp, vp, vp, vp, sz]
+    _lib.gsr_compact_gather.restype = ctypes.c_int
+    _lib.gsr_compact_gather.argtypes = [vp, i64, i64, i32, ctypes.POINTER(i32), vp, vp, i32, ctypes.POINTER(vp),
+                                        ctypes.POINTER(vp)]
 
 
 _bind()
@@ -193,23 +200,81 @@ class FlatAdam:
             off += v.numel()
         return out
 
+    def _relayout(self, keep, rows_out):
+        """One gsr_compact_gather pass: the kept rows of every group of parameters and both moments land in fresh flat
+        buffers laid out for `rows_out` rows per group.  Returns the new (flat, exp_avg, exp_avg_sq), the row widths
+        and the number of kept rows."""
+        if not self.flat.is_cuda:
+            raise RuntimeError("FlatAdam: CUDA tensors only (there is no CPU path)")
+        dev = self.flat.device
+        P = int(next(iter(self.views.values())).shape[0])
+        widths = []
+        for k in self.names:
+            w = 1
+            for d in self.views[k].shape[1:]:
+                w *= int(d)
+            widths.append(w)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            new_index, kept = None, P
+            if keep is not None:
+                if keep.shape != (P,) or keep.device != dev:
+                    raise RuntimeError("FlatAdam.prune: keep must be a [P] mask on the parameters' device")
+                k8 = keep.to(torch.uint8).contiguous() if keep.dtype != torch.uint8 else keep.contiguous()
+                new_index = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+                count = torch.empty(1, dtype=torch.int64, device=dev)
+                ws = torch.empty(_lib.gsr_compact_ws_bytes(P), dtype=torch.uint8, device=dev)
+                _check(_lib.gsr_compact_scan(stream, P, k8.data_ptr(), new_index.data_ptr(), count.data_ptr(),
+                                             ws.data_ptr(), ws.numel()))
+                kept = int(count.item())       # the one host hand-off: the new buffers are sized by it
+                if rows_out is None:
+                    rows_out = kept
+            wtot = sum(widths)
+            outs = [torch.empty(rows_out * wtot, dtype=torch.float32, device=dev) for _ in range(3)]
+            srcs = [self.flat, self.exp_avg, self.exp_avg_sq]
+            if P:
+                w_arr = (ctypes.c_int32 * len(widths))(*widths)
+                s_arr = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in srcs])
+                d_arr = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in outs])
+                _check(_lib.gsr_compact_gather(stream, P, rows_out, len(widths), w_arr,
+                                               k8.data_ptr() if keep is not None else None,
+                                               new_index.data_ptr() if keep is not None else None, 3, s_arr, d_arr))
+        return outs, widths, kept
+
+    def _adopt(self, outs, widths, rows):
+        self.flat, self.exp_avg, self.exp_avg_sq = outs
+        shapes = {k: (rows,) + tuple(self.views[k].shape[1:]) for k in self.names}
+        self.views, ends, off = {}, [], 0
+        for k, w in zip(self.names, widths):
+            self.views[k] = self.flat[off: off + rows * w].view(shapes[k])
+            off += rows * w
+            ends.append(off)
+        self.seg_end = (ctypes.c_int64 * len(ends))(*ends)
+        return self.views
+
     def prune(self, keep: torch.Tensor):
         """Keep the rows (dim 0 of every group) selected by the bool mask `keep`, parameters and both moments alike
-        (_prune_optimizer, R/slam/gaussian_model.py:380-399; the mapper calls it with ~prune_mask).  The step count is
-        kept.  Returns the new parameter views — the old ones are stale, as the reference's old Parameters are."""
-        m, v = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
-        return self._rehome({k: self.views[k][keep] for k in self.names}, {k: m[k][keep] for k in self.names},
-                            {k: v[k][keep] for k in self.names})
+        (_prune_optimizer, R/slam/gaussian_model.py:380-399; the mapper calls it with ~prune_mask): one mask scan + ONE
+        gather pass over the three flat buffers (gsr_compact_scan / gsr_compact_gather) instead of 21 boolean-index
+        kernels.  The step count is kept.  Returns the new parameter views — the old ones are stale, as the
+        reference's old Parameters are."""
+        outs, widths, kept = self._relayout(keep, None)
+        return self._adopt(outs, widths, kept)
 
     def extend(self, new: Dict[str, torch.Tensor]):
         """Append rows to every group; their moments start at zero and they share the running step count
-        (cat_tensors_to_optimizer, R/slam/gaussian_model.py:418-451).  Returns the new parameter views."""
+        (cat_tensors_to_optimizer, R/slam/gaussian_model.py:418-451).  The existing rows move to their place in the
+        longer layout in one gather pass; the appended rows are copied behind them.  Returns the new parameter views."""
+        P = int(next(iter(self.views.values())).shape[0])
+        A = int(next(iter(new.values())).shape[0])
+        outs, widths, _ = self._relayout(None, P + A)
+        views = self._adopt(outs, widths, P + A)
         m, v = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
-        cat = {k: torch.cat((self.views[k], new[k].detach().to(self.flat)), 0) for k in self.names}
-        return self._rehome(cat, {k: torch.cat((m[k], torch.zeros_like(new[k], dtype=torch.float32, device=self.flat.device)), 0)
-                                  for k in self.names},
-                            {k: torch.cat((v[k], torch.zeros_like(new[k], dtype=torch.float32, device=self.flat.device)), 0)
-                             for k in self.names})
+        for k in self.names:
+            views[k][P:].copy_(new[k].detach().to(self.flat).reshape(views[k][P:].shape))
+            m[k][P:].zero_()
+            v[k][P:].zero_()
+        return views
 
     def step(self, flat_grads: torch.Tensor, grad_scale: float = 1.0, zero_grads: bool = False):
         if not self.flat.is_cuda:

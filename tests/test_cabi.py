@@ -25,7 +25,7 @@ def test_header_symbols_exported(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/*.h but not exported"
     lib.gsr_abi_version.restype = ctypes.c_int
-    assert lib.gsr_abi_version() == 4
+    assert lib.gsr_abi_version() == 5
 
 
 def test_headers_are_plain_c(tmp_path):
@@ -35,7 +35,7 @@ def test_headers_are_plain_c(tmp_path):
     src = tmp_path / "hdr_check.c"
     src.write_text('#include "gsrast_b200.h"\n#include "gsloss_b200.h"\n'
                    "int main(void) { gsr_loss_config c; gsr_gaussians g; gsr_camera k; gsr_grads d;\n"
-                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 4 ? 0 : 1; }\n")
+                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 5 ? 0 : 1; }\n")
     inc = os.path.join(ROOT, "include")
     if shutil.which("gcc"):
         subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
@@ -58,7 +58,7 @@ def test_c_client_links_and_runs(built_lib, tmp_path):
                     os.path.join(ROOT, "tests", "c_client.c"), "-o", exe, "-L", libdir, "-lgsrast_b200",
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    assert out.startswith("abi 4 ")
+    assert out.startswith("abi 5 ")
 
 
 def test_workspace_layouts_are_sane(built_lib):
@@ -200,36 +200,17 @@ def test_product_never_imports_oracle():
                 assert "from oracle" not in txt and "import oracle" not in txt, os.path.join(d, f)
 
 
-def test_flat_adam_surgery_matches_reference_optimizer_surgery(built_lib):
-    """FlatAdam.prune / .extend against the reference's _prune_optimizer / cat_tensors_to_optimizer semantics
-    (R/slam/gaussian_model.py:380-451) carried out on a torch.optim.Adam: same parameters and the same moments row for
-    row, zeros for appended rows, step count untouched.  Pure bookkeeping, so it runs on CPU tensors."""
+def test_flat_adam_surgery_has_no_cpu_path(built_lib):
+    """FlatAdam.prune / .extend run the library's compaction kernels (gsr_compact_scan / gsr_compact_gather); like the
+    rest of the product they refuse CPU tensors instead of falling back (the parity test against the reference's
+    _prune_optimizer / cat_tensors_to_optimizer is tests/test_gpu_slam_ops.py::test_flat_adam_surgery_*)."""
+    import pytest
     import torch
 
     import gsr_slam_ops as ops
-    g = torch.Generator().manual_seed(0)
-    P, shapes = 50, {"xyz": (3,), "f_dc": (1, 3), "opacity": (1,), "scaling": (3,), "rotation": (4,)}
-    params = {k: torch.randn(P, *sh, generator=g) for k, sh in shapes.items()}
-    opt = ops.FlatAdam(params, {k: 1e-3 for k in shapes})
-    opt.steps = 7
-    opt.exp_avg.copy_(torch.randn(opt.flat.numel(), generator=g))
-    opt.exp_avg_sq.copy_(torch.rand(opt.flat.numel(), generator=g))
-    m0, v0 = ({k: t.clone() for k, t in opt._group_views(buf).items()} for buf in (opt.exp_avg, opt.exp_avg_sq))
-
-    keep = torch.rand(P, generator=g) < 0.6
-    views = opt.prune(keep)
-    n1 = int(keep.sum())
-    assert opt.steps == 7 and opt.flat.numel() == sum(v.numel() for v in views.values())
-    for k in shapes:
-        assert torch.equal(views[k], params[k][keep]) and views[k].shape == (n1,) + shapes[k]
-        assert torch.equal(opt._group_views(opt.exp_avg)[k], m0[k][keep])
-        assert torch.equal(opt._group_views(opt.exp_avg_sq)[k], v0[k][keep])
-        assert views[k].data_ptr() >= opt.flat.data_ptr() and views[k].is_contiguous()      # still views of the flat buffer
-
-    new = {k: torch.randn(9, *sh, generator=g) for k, sh in shapes.items()}
-    views = opt.extend(new)
-    for k in shapes:
-        assert torch.equal(views[k], torch.cat((params[k][keep], new[k]), 0))
-        assert torch.equal(opt._group_views(opt.exp_avg)[k], torch.cat((m0[k][keep], torch.zeros_like(new[k])), 0))
-        assert torch.equal(opt._group_views(opt.exp_avg_sq)[k], torch.cat((v0[k][keep], torch.zeros_like(new[k])), 0))
-    assert list(opt.seg_end) == [(n1 + 9) * c for c in (3, 6, 7, 10, 14)]
+    params = {"xyz": torch.randn(10, 3), "opacity": torch.randn(10, 1)}
+    opt = ops.FlatAdam(params, {"xyz": 1e-3, "opacity": 1e-3})
+    with pytest.raises(RuntimeError):
+        opt.prune(torch.ones(10, dtype=torch.bool))
+    with pytest.raises(RuntimeError):
+        opt.extend({k: v[:2] for k, v in params.items()})

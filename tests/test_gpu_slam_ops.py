@@ -215,3 +215,52 @@ def test_map_iteration_render_loss_adam(ops, built_lib):
             params["scales"].clamp_(min=1e-4)
         hist.append(float(losses[0]))
     assert hist[-1] < 0.95 * hist[0] and all(h == h for h in hist), hist     # measured ratio ~0.5; wide margin on purpose
+
+
+def _surgery_case(P, dev, seed=0):
+    import gsr_slam_ops as ops
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"xyz": (3,), "f_dc": (1, 3), "opacity": (1,), "scaling": (3,), "rotation": (4,)}
+    params = {k: torch.randn(P, *sh, generator=g).to(dev) for k, sh in shapes.items()}
+    opt = ops.FlatAdam(params, {k: 1e-3 for k in shapes})
+    opt.steps = 7
+    opt.exp_avg.copy_(torch.randn(opt.flat.numel(), generator=g))
+    opt.exp_avg_sq.copy_(torch.rand(opt.flat.numel(), generator=g))
+    m0, v0 = ({k: t.clone() for k, t in opt._group_views(buf).items()} for buf in (opt.exp_avg, opt.exp_avg_sq))
+    return opt, params, shapes, m0, v0, g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,frac", [(50, 0.6), (4096, 0.5), (4097, 0.999), (100003, 0.0), (100003, 1.0), (1000000, 0.7)])
+def test_flat_adam_surgery_matches_reference_optimizer_surgery(P, frac):
+    """FlatAdam.prune / .extend (one mask scan + one gather pass over parameters and both moments) against the
+    reference's _prune_optimizer / cat_tensors_to_optimizer semantics (R/slam/gaussian_model.py:380-451) carried out
+    with torch indexing / torch.cat: bit-identical rows, zeros for the moments of appended rows, step count untouched.
+    Edge cases: nothing kept, everything kept, row counts off the 4096-row scan chunk."""
+    dev = torch.device("cuda:0")
+    opt, params, shapes, m0, v0, g = _surgery_case(P, dev)
+    keep = (torch.rand(P, generator=g) < frac).to(dev)
+    views = opt.prune(keep)
+    n1 = int(keep.sum())
+    assert opt.steps == 7 and opt.flat.numel() == sum(v.numel() for v in views.values()) == 14 * n1
+    for k in shapes:
+        assert torch.equal(views[k], params[k][keep]) and views[k].shape == (n1,) + shapes[k]
+        assert torch.equal(opt._group_views(opt.exp_avg)[k], m0[k][keep])
+        assert torch.equal(opt._group_views(opt.exp_avg_sq)[k], v0[k][keep])
+        assert views[k].is_contiguous() and (n1 == 0 or views[k].data_ptr() >= opt.flat.data_ptr())
+    new = {k: torch.randn(9, *sh, generator=g).to(dev) for k, sh in shapes.items()}
+    views = opt.extend(new)
+    for k in shapes:
+        assert torch.equal(views[k], torch.cat((params[k][keep], new[k]), 0))
+        assert torch.equal(opt._group_views(opt.exp_avg)[k], torch.cat((m0[k][keep], torch.zeros_like(new[k])), 0))
+        assert torch.equal(opt._group_views(opt.exp_avg_sq)[k], torch.cat((v0[k][keep], torch.zeros_like(new[k])), 0))
+    assert list(opt.seg_end) == [(n1 + 9) * c for c in (3, 6, 7, 10, 14)]
+    # the optimizer keeps working on the re-laid-out buffers: one step equals torch.optim.Adam with the same state
+    grads = torch.randn(opt.flat.numel(), generator=g).to(dev)
+    ref_p = opt.flat.clone().requires_grad_(True)
+    ref_p.grad = grads.clone()
+    ref = torch.optim.Adam([ref_p], lr=1e-3, eps=1e-15)
+    ref.state[ref_p] = {"step": torch.tensor(7.0), "exp_avg": opt.exp_avg.clone(), "exp_avg_sq": opt.exp_avg_sq.clone()}
+    ref.step()
+    opt.step(grads)
+    assert float((opt.flat - ref_p.detach()).abs().max()) < 1e-6
