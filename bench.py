@@ -136,7 +136,7 @@ def stage_bytes(P, R, N, M=1):
     return {
         "preprocess_fwd": (g_in + 48) * P,
         "depth_sort": 8 * P,                       # SURVEY's "scan" row: the per-Gaussian ordering pass
-        "tile_partition": (12 + 24 + 8) * R,       # duplicate + ideal sort + range rows
+        "tile_partition": (12 + 24 + 8) * R,       # duplicate + ideal sort + range rows (tile_totals is folded into it)
         "render_fwd": 40 * R + 20 * N,
         "render_bwd": 76 * R + 20 * N,
         "preprocess_bwd": (g_in + 36 + 48 + g_in) * P,
@@ -690,12 +690,13 @@ def main():
     Rm = sum(R_mine) / max(len(R_mine), 1)
     sb = stage_bytes(P, Rm, N, (args.sh_degree + 1) ** 2)
     peak, peak_src = measured_peak()
-    stages = {}
+    stages, avg_ms = {}, {}
     for i in range(nst):
-        nm = lib.gsr_profile_stage_name(i).decode()
-        if cnt_arr[i] == 0:
-            continue
-        avg = ms_arr[i] / cnt_arr[i]
+        if cnt_arr[i]:
+            avg_ms[lib.gsr_profile_stage_name(i).decode()] = ms_arr[i] / cnt_arr[i]
+    if "tile_totals" in avg_ms:   # the per-tile count kernel belongs to the tile partition (it runs ahead of the sort)
+        avg_ms["tile_partition"] = avg_ms.get("tile_partition", 0.0) + avg_ms.pop("tile_totals")
+    for nm, avg in avg_ms.items():
         stages[nm] = {"ms": avg, "alg_bytes": sb[nm], "gbs": sb[nm] / (avg * 1e-3) / 1e9}
     total_ms = sum(s["ms"] for s in stages.values())
     dom = max(stages, key=lambda k: stages[k]["ms"])

@@ -37,6 +37,7 @@ constexpr int kSortItems = 8;                // keys per thread (4 measured slow
 constexpr int kSortChunk = kSortThreads * kSortItems;   // 4096 keys per CTA
 
 int sort_chunks(int P) { return (P + kSortChunk - 1) / kSortChunk; }
+__device__ __forceinline__ int sort_chunks_dev(int n) { return (n + kSortChunk - 1) / kSortChunk; }
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -118,12 +119,76 @@ constexpr int kRBins = 1 << kRadixBits;
 __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
+// Pass 0 additionally derives the per-tile instance counts from the tile rectangles (TileCount below): a splat adds one
+// instance to every tile of its rectangle [x0, x1) x [y0, y1), which as a 2-D difference array is four corner updates
+// per SPLAT (+1, -1, -1, +1) instead of one count per instance.  Every block accumulates them in shared memory (the
+// pass is a latency-bound walk whose load/store unit is otherwise idle), adds its non-zero cells to one of
+// kTileDiffReplicas global copies, and the block that finishes last sums the copies, integrates along x and y
+// (= instances per tile) and scans the tiles into ranges[t] = {start, end} and tile_starts[t] — ready long before the
+// tile partition runs, which can therefore place every instance at its final position in one kernel.
+struct TileCount {
+    const ushort4* rects;     // [P] tile rectangles
+    int gx, gy;
+    int* tile_diff;           // [kTileDiffReplicas][(gy+1)*(gx+1)], zero on entry
+    uint2* ranges;            // [T] out
+    uint32_t* tile_starts;    // [T] out
+};
+
+__device__ __forceinline__ void tile_ranges_from_diff(const TileCount& tc, int* cell, uint32_t* s_wsum, uint32_t* s_carry)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+    const int pitch = tc.gx + 1, rows = tc.gy + 1, cells = pitch * rows, T = tc.gx * tc.gy;
+    for (int c = tid; c < cells; c += nthreads) {
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < kTileDiffReplicas; k++) acc += __ldcg(tc.tile_diff + (size_t)k * cells + c);
+        cell[c] = acc;
+    }
+    __syncthreads();
+    for (int r = tid; r < rows; r += nthreads) {              // along x
+        int run = 0;
+        for (int x = 0; x < pitch; x++) { run += cell[r * pitch + x]; cell[r * pitch + x] = run; }
+    }
+    __syncthreads();
+    for (int x = tid; x < pitch; x += nthreads) {             // along y
+        int run = 0;
+        for (int r = 0; r < rows; r++) { run += cell[r * pitch + x]; cell[r * pitch + x] = run; }
+    }
+    if (tid == 0) *s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += nthreads) {
+        const int t = t0 + tid;
+        const uint32_t v = (t < T) ? (uint32_t)cell[(t / tc.gx) * pitch + (t % tc.gx)] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += s_wsum[w];
+        const uint32_t carry = *s_carry;
+        const uint32_t start = carry + wb + incl - v;
+        if (t < T) {
+            tc.tile_starts[t] = start;
+            tc.ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
+        }
+        __syncthreads();
+        if (tid == nthreads - 1) *s_carry = carry + wb + incl;
+        __syncthreads();
+    }
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* __restrict__ keys_in,
                                                                const uint2* __restrict__ pairs_in, int n_in,
                                                                const uint32_t* __restrict__ ghist, uint32_t* status,
-                                                               uint32_t* counters, uint2* __restrict__ pairs_out)
+                                                               uint32_t* counters, uint2* __restrict__ pairs_out,
+                                                               TileCount tc)
 {
+    extern __shared__ int s_tdiff[];                      // pass 0 only: this block's tile-count difference array
     __shared__ uint2 s_pairs[kSortChunk];                 // the block, reordered by digit (32 KB)
     __shared__ uint16_t s_cnt[kSortWarps][kRBins];        // per-warp digit counters -> exclusive prefix over the warps
     __shared__ uint32_t s_lstart[kRBins];                 // first local slot of each digit
@@ -140,6 +205,9 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
     const int block = (int)s_block;
     const int n = PASS == 0 ? n_in : (int)counters[kCntVisible];
     if (block * kSortChunk >= n) return;
+    const int tcells = PASS == 0 ? (tc.gx + 1) * (tc.gy + 1) : 0;
+    if (PASS == 0)
+        for (int i = tid; i < tcells; i += kSortThreads) s_tdiff[i] = 0;
 
     // each warp owns a contiguous sub-chunk; lanes hold consecutive elements of each 32-element batch
     const int wbase = block * kSortChunk + warp * (kSortChunk / kSortWarps);
@@ -157,6 +225,14 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
         }
     }
     reinterpret_cast<uint4*>(&s_cnt[warp][0])[lane] = make_uint4(0u, 0u, 0u, 0u);   // this warp's 256 counters
+    ushort4 rect[PASS == 0 ? kSortItems : 1];
+    if (PASS == 0) {
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const int i = wbase + j * 32 + lane;
+            rect[j] = (i < n && key[j] != 0xffffffffu) ? tc.rects[i] : make_ushort4(0, 0, 0, 0);
+        }
+    }
     // exclusive scan of the global digit histogram: where each digit's keys start in the output (threads < 256)
     uint32_t gstart = 0;
     if (tid < kRBins) {
@@ -175,6 +251,19 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
         for (int w = 0; w < warp; w++) gstart += s_warp[w];
         if (PASS == 0 && block == 0 && tid == kRBins - 1)          // number of visible Gaussians, for the later passes
             counters[kCntVisible] = gstart + ghist[kRBins - 1];
+    }
+    if (PASS == 0) {   // corner updates of the tile-count difference array (shared-memory atomics; s_tdiff was zeroed above)
+        const int pitch = tc.gx + 1;
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const ushort4 r = rect[j];
+            if (r.z > r.x && r.w > r.y) {
+                atomicAdd(&s_tdiff[r.y * pitch + r.x], 1);
+                atomicAdd(&s_tdiff[r.y * pitch + r.z], -1);
+                atomicAdd(&s_tdiff[r.w * pitch + r.x], -1);
+                atomicAdd(&s_tdiff[r.w * pitch + r.z], 1);
+            }
+        }
     }
 
     // rank inside the warp's sub-chunk: all matches first (independent: eight MATCH.ANY in flight), then ONE dependent
@@ -274,24 +363,53 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
         const uint2 kv = s_pairs[i];
         pairs_out[s_gdst[(kv.x >> shift) & mask] + i] = kv;
     }
+    if (PASS == 0) {
+        // flush this block's difference array; the block that finishes last turns the sums into the tile ranges
+        int* mine = tc.tile_diff + (size_t)(block % kTileDiffReplicas) * tcells;
+        for (int c = tid; c < tcells; c += kSortThreads) {
+            const int v = s_tdiff[c];
+            if (v != 0) atomicAdd(mine + c, v);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_block = (atomicAdd(&counters[kCntTotalsDone], 1u) == (uint32_t)(sort_chunks_dev(n) - 1)) ? 1u : 0u;
+        __syncthreads();
+        if (s_block) {
+            __threadfence();
+            tile_ranges_from_diff(tc, s_tdiff, s_lstart, &s_total);   // (s_lstart: 256 free words for the 16 warp sums)
+        }
+    }
 }
 
 template <int PASS>
 static void launch_sort_pass(const uint32_t* kin, const uint2* pin, int P, SortWS& w, uint32_t* counters, uint2* pout,
-                             cudaStream_t s)
+                             const TileCount& tc, cudaStream_t s)
 {
-    k_sort_pass<PASS><<<sort_chunks(P), kSortThreads, 0, s>>>(kin, pin, P, w.ghist, w.status, counters, pout);
+    const size_t smem = PASS == 0 ? sizeof(int) * (size_t)(tc.gx + 1) * (tc.gy + 1) : 0;
+    k_sort_pass<PASS><<<sort_chunks(P), kSortThreads, smem, s>>>(kin, pin, P, w.ghist, w.status, counters, pout, tc);
 }
 
-// Requires counters / ghist / status zeroed and ghist filled (k_preprocess_fwd).  Result: w.pairs_a holds the
-// counters[kCntVisible] visible Gaussians as {depth key, id} in (depth, index) order.
-void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, uint32_t* counters, cudaStream_t s)
+// Requires counters / ghist / status / tile_diff zeroed and ghist filled (k_preprocess_fwd).  Result: w.pairs_a holds
+// the counters[kCntVisible] visible Gaussians as {depth key, id} in (depth, index) order; ranges / w.tile_starts hold
+// every tile's place in the instance list.
+int launch_depth_sort(const uint32_t* depth_keys, const ushort4* rects, int P, int gx, int gy, SortWS& w, uint2* ranges,
+                      uint32_t* counters, cudaStream_t s)
 {
-    if (P <= 0) return;
-    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.pairs_b, s);
-    launch_sort_pass<1>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, s);
-    launch_sort_pass<2>(nullptr, w.pairs_a, P, w, counters, w.pairs_b, s);
-    launch_sort_pass<3>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, s);
+    if (P <= 0) return 0;
+    if (sizeof(int) * (size_t)(gx + 1) * (gy + 1) > 176 * 1024) return -1;   // tile grid too large for pass 0's shared memory
+    TileCount tc{rects, gx, gy, w.tile_diff, ranges, w.tile_starts};
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(k_sort_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+        configured[dev] = true;
+    }
+    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.pairs_b, tc, s);
+    launch_sort_pass<1>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, tc, s);
+    launch_sort_pass<2>(nullptr, w.pairs_a, P, w, counters, w.pairs_b, tc, s);
+    launch_sort_pass<3>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, tc, s);
+    return 0;
 }
 
 // ================================================================================================
@@ -355,89 +473,16 @@ __device__ __forceinline__ void load_rect(const uint2* __restrict__ perm, const 
     }
 }
 
-// Exclusive scan of the per-tile totals -> ranges[t] = {start, end}, starts[t].  One CTA of 1024 threads, any T.
-// (A heaviest-tiles-first launch order for the blend kernels was tried here and measured no gain on scenes whose
-// tiles carry similar loads; the blend kernels take tiles in index order.)
-__device__ __forceinline__ void cta_tile_starts(const uint32_t* totals, int T, uint2* __restrict__ ranges,
-                                                uint32_t* __restrict__ starts, uint32_t* s_warp, uint32_t* s_carry)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) *s_carry = 0;
-    __syncthreads();
-    for (int t0 = 0; t0 < T; t0 += 1024) {
-        const int t = t0 + tid;
-        const uint32_t v = (t < T) ? __ldcg(totals + t) : 0u;   // written by other CTAs of this launch
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t x = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= o) incl += x;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t wb = 0;
-        for (int w = 0; w < warp; w++) wb += s_warp[w];
-        const uint32_t carry = *s_carry;
-        const uint32_t start = carry + wb + incl - v;
-        if (t < T) {
-            starts[t] = start;
-            ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);   // empty tiles: {0,0} like the reference's memset
-        }
-        __syncthreads();
-        if (tid == 1023) *s_carry = carry + wb + incl;
-        __syncthreads();
-    }
-}
-
-// Column scan of H[chunks][bins]: in place H[c][b] <- sum_{c' < c} H[c'][b]; totals[b] <- sum_c H[c][b].
-// One CTA per 32 bins; the chunk axis is split into 32 segments handled by the 32 warps.  The CTA that finishes last
-// (ticket counter) turns the totals into the tile ranges, so the partition needs no separate launch for that.
-constexpr int kScanSegs = 32;
-__global__ void __launch_bounds__(32 * kScanSegs) k_column_scan(uint32_t* __restrict__ hist, int chunks, int bins,
-                                                                uint32_t* __restrict__ totals, uint2* __restrict__ ranges,
-                                                                uint32_t* __restrict__ starts,
-                                                                uint32_t* __restrict__ counters, uint32_t cap)
-{
-    __shared__ uint32_t s_seg[kScanSegs][32];
-    __shared__ uint32_t s_carry, s_last;
-    if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
-    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    const int b = blockIdx.x * 32 + lane;
-    const int per = (chunks + kScanSegs - 1) / kScanSegs;
-    const int c0 = min(seg * per, chunks), c1 = min(c0 + per, chunks);
-    uint32_t sum = 0;
-    if (b < bins)
-        for (int c = c0; c < c1; c++) sum += hist[(size_t)c * bins + b];
-    s_seg[seg][lane] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int s = 0; s < seg; s++) run += s_seg[s][lane];
-    if (b < bins) {
-        for (int c = c0; c < c1; c++) {
-            const size_t o = (size_t)c * bins + b;
-            const uint32_t v = hist[o];
-            hist[o] = run;
-            run += v;
-        }
-        if (seg == kScanSegs - 1) totals[b] = run;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[kCntScanDone], 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        cta_tile_starts(totals, bins, ranges, starts, &s_seg[0][0], &s_carry);
-    }
-}
-
 // Rank of this lane's instance among the instances of the same tile this warp has seen so far, and count it.
 // `cnt` / `tag`: the warp's private per-tile counters (16 bit) and scratch bytes in shared memory.  The instances
 // of a step come from a handful of neighbouring splats and a splat's tiles are distinct, so two lanes rarely
 // hold the same tile: every lane writes its lane id to tag[tile] and reads it back — if nobody lost that race all
 // tiles are distinct and the rank is a plain (non-atomic) read-increment-write; only otherwise are same-tile lanes
 // matched (one ballot per tile-id bit) and ranked in lane order.  No shared-memory atomics (2 cycles per lane).
-__device__ __forceinline__ uint32_t warp_rank_tile(uint16_t* cnt, uint8_t* tag, uint32_t tile, bool valid, int tbits)
+// `delta` (the same for every lane of a call): what each instance adds to its counter — 1 for ranking, +-1 (mod 2^16)
+// for the corner updates of a difference array.
+__device__ __forceinline__ uint32_t warp_rank_tile(uint16_t* cnt, uint8_t* tag, uint32_t tile, bool valid, int tbits,
+                                                   uint32_t delta = 1u)
 {
     const int lane = threadIdx.x & 31;
     if (valid) tag[tile] = (uint8_t)lane;
@@ -446,30 +491,34 @@ __device__ __forceinline__ uint32_t warp_rank_tile(uint16_t* cnt, uint8_t* tag, 
     const uint32_t old = valid ? cnt[tile] : 0u;
     uint32_t rank = old;
     if (!__any_sync(kFullMask, lost)) {
-        if (valid) cnt[tile] = (uint16_t)(old + 1u);
+        if (valid) cnt[tile] = (uint16_t)(old + delta);
     } else {
         const unsigned peers = match_any_bits(tile, valid, tbits);
         __syncwarp();
-        if (valid && lane == __ffs(peers) - 1) cnt[tile] = (uint16_t)(old + __popc(peers));
+        if (valid && lane == __ffs(peers) - 1) cnt[tile] = (uint16_t)(old + delta * (uint32_t)__popc(peers));
         rank = old + __popc(peers & lanemask_lt());
     }
     __syncwarp();
     return rank;
 }
 
-// Pass A.  A CTA owns a contiguous chunk of depth-ordered Gaussians.  It loads their tile rectangles,
-// scans the instance counts in shared memory and gives every warp an EQUAL share of the chunk's
+// The tile partition.  ONE kernel: the per-tile instance counts (and with them every tile's range in the final list)
+// are already known — k_preprocess_fwd accumulates them as a 2-D difference array and its last CTA integrates it —
+// so the only global information a CTA lacks is how many instances of each tile belong to the CTAs before it, and
+// that arrives by decoupled look-back over per-tile rows (the depth sort's scheme with T bins instead of 256).
+//
+// A CTA takes a ticket c and owns the c-th contiguous chunk of depth-ordered Gaussians.  It loads their tile
+// rectangles, scans the instance counts in shared memory and gives every warp an EQUAL share of the chunk's
 // instances (a share may start and end in the middle of a splat — a splat's tiles are distinct, so any
 // cut keeps the per-tile order intact).  Splats covering hundreds of tiles would otherwise serialise
 // the one warp that owns them.  Each warp enumerates its share twice:
 //   phase 1 counts its instances per tile (private 16-bit counters for all T tiles in shared memory — what the
-//           B200's 227 KB buys); then, per tile, the counts are prefixed over the CTA's warps and their sum
-//           becomes row c of the histogram matrix H;
+//           B200's 227 KB buys); per tile, the counts are then prefixed over the CTA's warps, their sum is published
+//           as row c of the look-back state and the look-back returns the number of earlier instances of the tile;
 //   phase 2 ranks every instance among the CTA's earlier instances of the same tile (prefix + running count) and
-//           writes one {tile | rank << 16, Gaussian id} record into a segment of the instance stream claimed with
-//           one atomicAdd (segments may sit anywhere in the stream; only their contents are ordered).
-// Nothing is read back: pass B only adds the two global prefixes.
-// Dynamic shared memory: uint32 s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1]; uint16 s_cnt[nwarps][T];
+//           stores its Gaussian id at  point_list[tile start + earlier CTAs + rank]  — the final position.
+// No intermediate instance stream, no histogram matrix scan, no second kernel.
+// Dynamic shared memory: uint32 s_id[per_cta], s_pk[per_cta], s_ex[per_cta + 1], s_base[T]; uint16 s_cnt[nwarps][T];
 // uint8 s_tag[nwarps][T].
 template <typename F>
 __device__ __forceinline__ void warp_share_for_each(const uint32_t* s_id, const uint32_t* s_pk, const uint32_t* s_ex,
@@ -498,29 +547,38 @@ __device__ __forceinline__ void warp_share_for_each(const uint32_t* s_id, const 
     }
 }
 
-__global__ void __launch_bounds__(1024) k_tile_rank(const uint2* __restrict__ perm, int per_cta,
-                                                   const ushort4* __restrict__ rects, int gx, int T,
-                                                   uint32_t* __restrict__ hist, uint2* __restrict__ stream,
-                                                   uint2* __restrict__ segs, uint32_t* __restrict__ counters, uint32_t cap)
+constexpr uint32_t kTileAgg = 1u << 30, kTileIncl = 2u << 30, kTileVal = (1u << 30) - 1u;
+constexpr int kTileLook = 8;     // predecessors per look-back step
+
+__global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict__ perm, int per_cta,
+                                                        const ushort4* __restrict__ rects, int gx, int T,
+                                                        uint32_t* status, const uint32_t* __restrict__ tile_starts,
+                                                        uint32_t* __restrict__ point_list, uint32_t* __restrict__ counters,
+                                                        uint32_t cap)
 {
     if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
     const int n = (int)counters[kCntVisible];          // the depth sort kept only the visible Gaussians
-    uint32_t* claim = counters + kCntClaim;
     extern __shared__ uint32_t s_dyn[];
+    __shared__ uint32_t s_wsum[32];
+    __shared__ int s_block;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (tid == 0) s_block = (int)atomicAdd(&counters[kCntPartTicket], 1u);
+    __syncthreads();
+    const int block = s_block;
+    const int c0 = block * per_cta;
+    if (c0 >= n) return;                   // (so is every later ticket: nobody will look back at this row)
     uint32_t* s_id = s_dyn;
     uint32_t* s_pk = s_id + per_cta;
     uint32_t* s_ex = s_pk + per_cta;       // [per_cta + 1] exclusive instance offsets inside the chunk
+    uint32_t* s_base = s_ex + ((per_cta + 1 + 3) & ~3);
     const int Tp = (T + 7) & ~7;           // row pitch: keeps every row 16-byte aligned
-    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_ex + ((per_cta + 1 + 3) & ~3));
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_base + Tp);
     uint8_t* s_tag = reinterpret_cast<uint8_t*>(s_cnt + (size_t)nwarps * Tp);
-    __shared__ uint32_t s_wsum[32];
     {   // zero the counters (the tags need no initial value)
         uint4* z = reinterpret_cast<uint4*>(s_cnt);
         const int n16 = nwarps * Tp / 8;
         for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    const int c0 = blockIdx.x * per_cta;
     const int m = min(per_cta, n - c0);    // Gaussians in this chunk
     // load + block-wide exclusive scan of the counts (thread t owns the contiguous slice [t*q, (t+1)*q))
     const int q = (per_cta + blockDim.x - 1) / blockDim.x;
@@ -558,12 +616,6 @@ __global__ void __launch_bounds__(1024) k_tile_rank(const uint2* __restrict__ pe
     // this warp's share [a, b) of the chunk's S instances
     const uint32_t a = (uint32_t)(((uint64_t)S * warp) / nwarps), b = (uint32_t)(((uint64_t)S * (warp + 1)) / nwarps);
     const uint32_t len = b - a;
-    uint32_t seg = 0;
-    if (lane == 0) {
-        seg = len ? atomicAdd(claim, len) : 0u;
-        segs[(size_t)blockIdx.x * nwarps + warp] = make_uint2(seg, len);
-    }
-    seg = __shfl_sync(kFullMask, seg, 0);
     int first = 0;
     if (len != 0) {
         // first splat of the share: last g with s_ex[g] <= a  (s_ex is non-decreasing; zero-count splats only at the end)
@@ -583,8 +635,9 @@ __global__ void __launch_bounds__(1024) k_tile_rank(const uint2* __restrict__ pe
             warp_rank_tile(my, my_tag, tile, valid, tbits);
         });
     __syncthreads();
-    uint32_t* row = hist + (size_t)blockIdx.x * T;
-    for (int t = tid; t < T; t += blockDim.x) {     // per tile: exclusive prefix over the warps, total -> H[c][t]
+    // per tile: exclusive prefix over the warps; the sum is this CTA's count -> publish, look back, final base
+    uint32_t* my_status = status + (size_t)block * T;
+    for (int t = tid; t < T; t += blockDim.x) {
         uint32_t acc = 0;
 #pragma unroll 8
         for (int w = 0; w < nwarps; w++) {
@@ -592,59 +645,57 @@ __global__ void __launch_bounds__(1024) k_tile_rank(const uint2* __restrict__ pe
             s_cnt[(size_t)w * Tp + t] = (uint16_t)acc;
             acc += c;
         }
-        row[t] = acc;
+        st_status(my_status + t, (block == 0 ? kTileIncl : kTileAgg) | acc);
+        s_base[t] = acc;
+    }
+    for (int t = tid; t < T; t += blockDim.x) {
+        const uint32_t agg = s_base[t];
+        uint32_t excl = 0;
+        int p = block - 1;
+        while (p >= 0) {   // kTileLook predecessors per step; block 0 always publishes an inclusive value
+            uint32_t v[kTileLook];
+#pragma unroll
+            for (int u = 0; u < kTileLook; u++)
+                v[u] = (p - u >= 0) ? ld_status(status + (size_t)(p - u) * T + t) : kTileIncl;
+            int used = 0;
+            bool done = false, stalled = false;
+#pragma unroll
+            for (int u = 0; u < kTileLook; u++) {
+                if (done || stalled) continue;
+                const uint32_t tag = v[u] & ~kTileVal;
+                if (tag == kTileIncl) {
+                    excl += v[u] & kTileVal;
+                    done = true;
+                } else if (tag == kTileAgg) {
+                    excl += v[u] & kTileVal;
+                    used++;
+                } else {
+                    stalled = true;
+                }
+            }
+            if (done) break;
+            p -= used;
+            if (stalled) __nanosleep(40);
+        }
+        if (block > 0) st_status(my_status + t, kTileIncl | (excl + agg));
+        s_base[t] = tile_starts[t] + excl;
     }
     __syncthreads();
-    if (len != 0) {
-        uint2* out = stream + seg;
-        warp_share_for_each(s_id, s_pk, s_ex, per_cta, first, a, b, gx, [&](uint32_t tile, uint32_t gid, bool valid, uint32_t i) {
+    if (len != 0)
+        warp_share_for_each(s_id, s_pk, s_ex, per_cta, first, a, b, gx, [&](uint32_t tile, uint32_t gid, bool valid, uint32_t) {
             const uint32_t rank = warp_rank_tile(my, my_tag, tile, valid, tbits);
-            if (valid) out[i] = make_uint2(tile | (rank << 16), gid);
+            if (valid) point_list[s_base[tile] + rank] = gid;
         });
-    }
-}
-
-// Pass B.  Same CTA / warp <-> segment mapping as pass A; every warp streams its segment once with coalesced
-// 8-byte loads (four steps in flight): point_list[start[tile] + H[c][tile] + rank] = Gaussian id.
-// Dynamic shared memory: uint32 s_start[T].
-__global__ void __launch_bounds__(1024) k_tile_scatter(int T, const uint32_t* __restrict__ base,
-                                                      const uint32_t* __restrict__ starts, const uint2* __restrict__ stream,
-                                                      const uint2* __restrict__ segs, uint32_t* __restrict__ point_list,
-                                                      const uint32_t* __restrict__ counters, uint32_t cap)
-{
-    extern __shared__ uint32_t s_dyn[];
-    if (counters[kCntR] > cap) return;
-    uint32_t* s_start = s_dyn;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t* row = base + (size_t)blockIdx.x * T;
-    const uint2 seg = segs[(size_t)blockIdx.x * nwarps + warp];
-    for (int t = tid; t < T; t += blockDim.x) s_start[t] = starts[t] + row[t];
-    __syncthreads();
-    const uint2* my_stream = stream + seg.x;
-    const uint32_t len = seg.y;
-    for (uint32_t b0 = 0; b0 < len; b0 += 128) {
-        uint2 r[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t i = b0 + u * 32 + lane;
-            r[u] = (i < len) ? __ldcs(my_stream + i) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t i = b0 + u * 32 + lane;
-            if (i < len) point_list[s_start[r[u].x & 0xffffu] + (r[u].x >> 16)] = r[u].y;
-        }
-    }
 }
 
 // Chunking of the tile partition: ranks are 16 bit and relative to the CTA, so a CTA may own at most 65535
-// Gaussians; the CTA count is capped so that the H matrix stays small.
-static size_t tile_rank_smem(int T, int per_cta, int warps)
+// Gaussians; the CTA count is capped so that the look-back state stays small.
+static size_t tile_partition_smem(int T, int per_cta, int warps)
 {
     const size_t Tp = (size_t)((T + 7) & ~7);
-    return (size_t)(2 * per_cta + ((per_cta + 1 + 3) & ~3)) * 4 + Tp * 3 * (size_t)warps;
+    return (size_t)(2 * per_cta + ((per_cta + 1 + 3) & ~3)) * 4 + Tp * 4 + Tp * 3 * (size_t)warps;
 }
-void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem_count, size_t& smem_scatter)
+void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem)
 {
     // as many warps per CTA as their private per-tile counters (3 bytes per tile) allow in ~200 KB of shared memory
     // next to the chunk's rectangles, at most 32: the kernel is a latency-bound walk, so short per-warp shares matter
@@ -656,38 +707,34 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
         if (per_cta < 1024) per_cta = 1024;
         if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
         per_cta = (per_cta + 31) / 32 * 32;
-        while (tile_rank_smem(T, per_cta, warps) > 200 * 1024 && per_cta > 1024) per_cta = (per_cta / 2 + 31) / 32 * 32;
-        if (tile_rank_smem(T, per_cta, warps) <= 200 * 1024 || warps == 1) break;
+        while (tile_partition_smem(T, per_cta, warps) > 200 * 1024 && per_cta > 1024) per_cta = (per_cta / 2 + 31) / 32 * 32;
+        if (tile_partition_smem(T, per_cta, warps) <= 200 * 1024 || warps == 1) break;
         warps >>= 1;
     }
-    if (tile_rank_smem(T, per_cta, warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
+    if (tile_partition_smem(T, per_cta, warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
     ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
-    smem_count = tile_rank_smem(T, per_cta, warps > 0 ? warps : 1);
-    smem_scatter = (size_t)T * 4;
+    smem = tile_partition_smem(T, per_cta, warps > 0 ? warps : 1);
 }
 
-// `cap`: number of instances the caller's stream / point_list arrays can hold.  If the scene has more (counters[kCntR],
-// known on the device only), every kernel here returns without touching them.
-int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint2* stream, uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s)
+// `cap`: number of instances the caller's point_list can hold.  If the scene has more (counters[kCntR], known on the
+// device only), the kernel returns without touching it.
+int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w,
+                          uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;
     int ctas, per_cta, warps;
-    size_t smem_c, smem_s;
-    tile_partition_plan(P, T, ctas, per_cta, warps, smem_c, smem_s);
-    if (warps == 0 || smem_s > 220 * 1024 || smem_c > 220 * 1024 || per_cta > 65535) return -1;   // image / scene too large
+    size_t smem;
+    tile_partition_plan(P, T, ctas, per_cta, warps, smem);
+    if (warps == 0 || smem > 220 * 1024 || per_cta > 65535) return -1;   // image / scene too large
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {   // opt in to the large B200 carve-out once per device
-        cudaFuncSetAttribute(k_tile_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_tile_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         configured[dev] = true;
     }
-    k_tile_rank<<<ctas, warps * 32, smem_c, s>>>(perm, per_cta, rects, gx, T, w.tile_hist, stream, w.segs, counters, cap);
-    k_column_scan<<<(T + 31) / 32, 32 * kScanSegs, 0, s>>>(w.tile_hist, ctas, T, w.tile_totals, ranges, w.tile_starts,
-                                                           counters, cap);
-    k_tile_scatter<<<ctas, warps * 32, smem_s, s>>>(T, w.tile_hist, w.tile_starts, stream, w.segs, point_list, counters, cap);
+    k_tile_partition<<<ctas, warps * 32, smem, s>>>(perm, per_cta, rects, gx, T, w.tile_status, w.tile_starts, point_list,
+                                                    counters, cap);
     return 0;
 }
 

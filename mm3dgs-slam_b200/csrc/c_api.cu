@@ -102,10 +102,15 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.rec = carve<float4>(p, n * 3);
     w.rects = carve<ushort4>(p, n);
     w.depth_keys = carve<uint32_t>(p, n);
-    // counters | ghist are contiguous: one small memset zeroes them at the start of a forward (the projection kernel
-    // adds to both); the sort's look-back state is zeroed by the projection kernel itself
+    // counters | ghist | tile_diff | tile_status are contiguous: one memset zeroes them at the start of a forward (the
+    // projection kernel adds to the first three); the sort's look-back state is zeroed by the projection kernel itself
+    int ctas, per_cta, warps;
+    size_t smem;
+    tile_partition_plan((int)n, T, ctas, per_cta, warps, smem);
     w.counters = carve<uint32_t>(p, 64);          // [63] = CTA counter of the camera-gradient reduction
     w.sort.ghist = carve<uint32_t>(p, kSortDigits * kSortBins);
+    w.sort.tile_diff = carve<int>(p, (size_t)kTileDiffReplicas * ((W + kTile - 1) / kTile + 1) * ((H + kTile - 1) / kTile + 1));
+    w.sort.tile_status = carve<uint32_t>(p, (size_t)ctas * T);
     w.zero_bytes = (size_t)(p - reinterpret_cast<char*>(w.counters));
     w.sort.status_words = (size_t)sort_chunks((int)n) * kSortBins;
     w.sort.status = carve<uint32_t>(p, w.sort.status_words);
@@ -113,13 +118,7 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.sort.pairs_a = carve<uint2>(p, n);
     w.sort.pairs_b = carve<uint2>(p, n);
     w.cam_partials = carve<double>(p, (size_t)kCamPartialRows * 35);
-    int ctas, per_cta, warps;
-    size_t sc, ss;
-    tile_partition_plan((int)n, T, ctas, per_cta, warps, sc, ss);
-    w.sort.tile_hist = carve<uint32_t>(p, (size_t)ctas * T);
-    w.sort.tile_totals = carve<uint32_t>(p, (size_t)T);
     w.sort.tile_starts = carve<uint32_t>(p, (size_t)T);
-    w.sort.segs = carve<uint2>(p, (size_t)ctas * 32);
     w.total = (size_t)(p - base);
     return w;
 }
@@ -142,7 +141,6 @@ BinWS bin_ws_carve(char* base, int64_t R)
     BinWS w;
     char* p = base;
     w.point_list = carve<uint32_t>(p, R > 0 ? (size_t)R : 1);
-    w.stream = carve<uint2>(p, R > 0 ? (size_t)R : 1);
     w.contrib = carve<uint8_t>(p, R > 0 ? (size_t)R : 1);
     w.total = (size_t)(p - base);
     return w;
@@ -280,7 +278,8 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     a.chunk_ticket = gw.counters + kCntChunkFwd;
     a.extra_gen = g->extra_mode == 1 ? gw.extra_gen : nullptr;
     prof_mark(ST_BEGIN, stream);
-    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, gw.zero_bytes, stream));   // counters + digit histograms (4 KB)
+    // counters, digit histograms, tile-count difference array, look-back state of the tile partition (a few MB)
+    GSR_CUDA(cudaMemsetAsync(gw.counters, 0, gw.zero_bytes, stream));
     launch_preprocess_fwd(a, stream);
     GSR_STAGE("preprocess", cam->debug, stream);
     GSR_MARK(ST_PREPROCESS, stream, 1);
@@ -292,7 +291,11 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
         GSR_CUDA(cudaMemcpyAsync(hs.pinned, gw.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         GSR_CUDA(cudaEventRecord(hs.ev, stream));
     }
-    launch_depth_sort(gw.depth_keys, P, gw.sort, gw.counters, stream);
+    // (pass 0 also derives the per-tile instance counts and tile ranges from the rectangles, so that the tile
+    // partition can place every instance at its final position in one kernel)
+    if (launch_depth_sort(gw.depth_keys, gw.rects, P, a.gx, a.gy, gw.sort, img_ws_carve((char*)img_ws, W, H).ranges,
+                          gw.counters, stream) != 0)
+        return fail(GSR_ERR_INVALID, "tile grid too large (more than ~45k tiles)");
     GSR_STAGE("depth_sort", cam->debug, stream);
     GSR_MARK(ST_DEPTH_SORT, stream, 4);
     if (async_r) {
@@ -333,11 +336,11 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (launch_tile_partition(gw.sort.pairs_a, P, gw.rects, gx, gy, gw.sort, iw.ranges, bw.stream, gw.counters, (uint32_t)R,
-                              bw.point_list, stream) != 0)
+    if (launch_tile_partition(gw.sort.pairs_a, P, gw.rects, gx, gy, gw.sort, gw.counters, (uint32_t)R, bw.point_list,
+                              stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
-    GSR_MARK(ST_TILE_PARTITION, stream, 3);
+    GSR_MARK(ST_TILE_PARTITION, stream, 1);
     launch_render_fwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,
                       out_color, bw.contrib, g->extra_mode == 1 ? gw.extra_gen : g->extra_colors, out_extra,
                       gw.counters, (uint32_t)R, stream);

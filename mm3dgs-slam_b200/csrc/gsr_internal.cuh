@@ -26,19 +26,20 @@ constexpr int kCntVisible = 2;   // number of visible Gaussians (= length of the
 constexpr int kCntTicket = 3;    // [4] block tickets of the four depth-sort passes (slots 3..6)
 constexpr int kCntChunkFwd = 8;  // chunk ticket of k_preprocess_fwd
 constexpr int kCntChunkBwd = 9;  // chunk ticket of k_preprocess_bwd (wraps to zero by itself)
-constexpr int kCntScanDone = 10; // CTAs of the tile partition's column scan that have finished
+constexpr int kCntTotalsDone = 10; // blocks of depth-sort pass 0 that have finished (the last one builds the tile ranges)
+constexpr int kCntPartTicket = 11; // block ticket of the tile partition
 constexpr int kSortDigits = 4;   // 8-bit digits of the depth sort
 constexpr int kSortBins = 256;
+constexpr int kTileDiffReplicas = 8;   // copies of the tile-count difference array (spreads the flush REDs)
 
 struct SortWS {
     uint2 *pairs_a, *pairs_b;                      // depth-sort ping-pong of {depth key, Gaussian id} (P each); result in pairs_a
     uint32_t* ghist;                               // [4][256] global digit histograms of the visible depth keys
     uint32_t* status;                              // [sort_chunks(P)][256] look-back state of the sort passes
     size_t status_words;
-    uint32_t* tile_hist;                           // [partition CTAs][T]
-    uint32_t* tile_totals;                         // [T]
-    uint32_t* tile_starts;                         // [T]
-    uint2* segs;                                   // [partition CTAs * warps] {stream offset, length}
+    int* tile_diff;                                // [kTileDiffReplicas][(gy+1)*(gx+1)] difference arrays of the per-tile instance counts
+    uint32_t* tile_status;                         // [partition CTAs][T] look-back state of the tile partition
+    uint32_t* tile_starts;                         // [T] first list position of every tile
 };
 constexpr int kCamPartialRows = 1024;   // >= the grid of k_preprocess_bwd (2 CTAs per SM)
 struct GeomWS {
@@ -60,7 +61,6 @@ struct ImgWS {
 };
 struct BinWS {
     uint32_t* point_list;   // [R] final per-tile, depth-ordered Gaussian ids
-    uint2* stream;          // [R] {tile | rank << 16, Gaussian id} in enumeration order (scratch of the partition)
     uint8_t* contrib;       // [R] per list entry: which of the tile's 8 warps blended it in the forward
     size_t total;
 };
@@ -69,7 +69,7 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H);
 ImgWS img_ws_carve(char* base, int W, int H);
 BinWS bin_ws_carve(char* base, int64_t R);
 int sort_chunks(int P);
-void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem_count, size_t& smem_scatter);
+void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size_t& smem);
 
 // ---- launchers (each enqueues on `s`) ---------------------------------------------------------
 struct PreArgs {
@@ -91,9 +91,10 @@ void launch_preprocess_fwd(const PreArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, const float* proj, uint8_t* present,
                          cudaStream_t s);
 
-void launch_depth_sort(const uint32_t* depth_keys, int P, SortWS& w, uint32_t* counters, cudaStream_t s);
-int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w, uint2* ranges,
-                          uint2* stream, uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s);
+int launch_depth_sort(const uint32_t* depth_keys, const ushort4* rects, int P, int gx, int gy, SortWS& w, uint2* ranges,
+                      uint32_t* counters, cudaStream_t s);
+int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w,
+                          uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s);
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,
                        const float4* rec, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color,

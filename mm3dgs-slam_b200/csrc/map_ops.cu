@@ -168,9 +168,9 @@ int gsr_compact_gather(gsr_stream_t stream_, int64_t P, int64_t rows_out, int32_
     for (int b = 0; b < GSR_COMPACT_MAX_BUFFERS; b++) {
         a.src[b] = b < nbuf ? src[b] : nullptr;
         a.dst[b] = b < nbuf ? dst[b] : nullptr;
-        if (b < nbuf && (!src[b] || !dst[b]) && P > 0) return api_fail(GSR_ERR_INVALID, "null buffer");
+        if (b < nbuf && P > 0 && (!src[b] || (!dst[b] && rows_out > 0))) return api_fail(GSR_ERR_INVALID, "null buffer");
     }
-    if (P == 0) return GSR_OK;
+    if (P == 0 || rows_out == 0) return GSR_OK;
     long long bx = ((long long)P * wmax + 255) / 256;
     const long long cap = (long long)device_sm_count() * 8;
     if (bx > cap) bx = cap;
