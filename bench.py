@@ -540,7 +540,8 @@ def main():
                                  # (overwrite_first measured slower here: its per-frame backward calls make autograd
                                  #  re-join the streams after every frame: 1705 vs 1861 frames/s)
                                  overwrite_first=bool(os.environ.get("GSR_BENCH_OVERWRITE")),
-                                 prepare_fn=None if os.environ.get("GSR_BENCH_NO_PREPARE") else prepare_fn)
+                                 prepare_fn=None if os.environ.get("GSR_BENCH_NO_PREPARE") else prepare_fn,
+                                 exchange=os.environ.get("GSR_EXCHANGE", "auto"))
         step = lambda: stepper.step(kfs)  # noqa: E731
         launch_count = dgr._lib.gsr_launch_count
         launch_count.restype = ctypes.c_longlong
@@ -650,6 +651,9 @@ def main():
         return 0
 
     line["gpu_launches"] = int(n1 - n0) // max(1, len(block_ms))      # per timed block of --steps steps
+    line["run"]["exchange"] = stepper.exchange if world > 1 else "none (1 rank)"
+    if stepper.exchange_error:
+        line["run"]["exchange_fallback_reason"] = stepper.exchange_error
     line["run"]["R_mean"] = sum(R_list) / max(len(R_list), 1)
     line["run"]["visible_mean"] = sum(vis_list) / max(len(vis_list), 1)
 

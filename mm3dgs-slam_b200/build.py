@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libgsrast_b200.so")
-SOURCES = ["preprocess.cu", "preprocess_bwd.cu", "binning.cu", "render.cu", "slam_ops.cu", "map_ops.cu", "c_api.cu"]
+SOURCES = ["preprocess.cu", "preprocess_bwd.cu", "binning.cu", "render.cu", "slam_ops.cu", "map_ops.cu", "comm.cu", "c_api.cu"]
 # per-file extra flags.  (--use_fast_math on preprocess_bwd.cu — legal there, nothing in the backward feeds an
 # integer output — was measured SLOWER on B200: 74 vs 64 registers, 106 vs 95 us; so everything uses nvcc defaults.)
 EXTRA_FLAGS = {"preprocess_bwd.cu": ["--use_fast_math"] if os.environ.get("GSR_FAST_BWD") else []}
@@ -29,7 +29,7 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 
 def _deps():
     d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    d += [os.path.join(HERE, "..", "include", h) for h in ("gsrast_b200.h", "gsloss_b200.h")]
+    d += [os.path.join(HERE, "..", "include", h) for h in ("gsrast_b200.h", "gsloss_b200.h", "gscomm_b200.h")]
     return d
 
 

@@ -21,15 +21,70 @@ import torch
 import torch.distributed as dist
 
 
-class GradBucket:
-    """One flat fp32 tensor holding the gradients of all parameters, exposed as per-parameter views."""
+class PeerExchange:
+    """The gradient exchange over peer memory (include/gscomm_b200.h): the bucket lives in a symmetric allocation that
+    every rank of the node maps (torch.distributed._symmetric_memory does the handle exchange — plumbing), and ONE
+    library kernel per step pulls, reduces and broadcasts it over NVLink (multimem instructions through the NVSwitch
+    when the node has NVLS).  No NCCL call on the path.  Raises if symmetric memory cannot be set up; the caller then
+    stays on NCCL's all_reduce."""
 
-    def __init__(self, params: Dict[str, torch.Tensor]):
+    def __init__(self, n: int, device, group=None, mode: str = "auto"):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from diff_gaussian_rasterization import _lib
+        self._lib, self._ct = _lib, ctypes
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(grp), dist.get_rank(grp)
+        if self.world not in (2, 4, 8):
+            raise RuntimeError("peer exchange needs 2, 4 or 8 ranks")
+        _lib.gsr_allreduce_flag_words.restype = ctypes.c_size_t
+        _lib.gsr_allreduce_sum_f32.restype = ctypes.c_int
+        _lib.gsr_allreduce_sum_f32.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+                                               ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64, ctypes.c_uint32]
+        self.n = n
+        n_pad = (n + 3) // 4 * 4
+        self._store = symm_mem.empty(n_pad, dtype=torch.float32, device=device)
+        self._store.zero_()
+        self._h = symm_mem.rendezvous(self._store, grp)
+        words = int(_lib.gsr_allreduce_flag_words())
+        self._flags = symm_mem.empty(words, dtype=torch.int32, device=device)
+        self._flags.zero_()
+        self._hf = symm_mem.rendezvous(self._flags, grp)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=grp)                       # every rank's flags are zero before anybody's first handshake
+        self.flat = self._store[:n]
+        mc = int(self._h.multicast_ptr) if mode in ("auto", "nvls") else 0
+        if mode == "nvls" and not mc:
+            raise RuntimeError("no multicast (NVLS) mapping on this node")
+        self.mode = "nvls" if mc else "peer"
+        self._mc = mc or None
+        self._bp = (ctypes.c_void_p * self.world)(*[int(p) for p in self._h.buffer_ptrs])
+        self._fp = (ctypes.c_void_p * self.world)(*[int(p) for p in self._hf.buffer_ptrs])
+        self.epoch = 0
+
+    def all_reduce(self):
+        """SUM over the ranks, in place, on torch's current stream; nothing waits on the host."""
+        self.epoch += 1
+        rc = self._lib.gsr_allreduce_sum_f32(torch.cuda.current_stream(self.flat.device).cuda_stream, self.world, self.rank,
+                                             self._bp, self._mc, self._fp, self.n, self.epoch)
+        if rc != 0:
+            raise RuntimeError("gsrast_b200: " + self._lib.gsr_last_error().decode())
+
+
+class GradBucket:
+    """One flat fp32 tensor holding the gradients of all parameters, exposed as per-parameter views.
+    `flat`: storage to use (e.g. PeerExchange.flat) instead of a fresh allocation."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], flat: Optional[torch.Tensor] = None):
         self.names = list(params.keys())
         self.params = params
         n = sum(p.numel() for p in params.values())
         first = next(iter(params.values()))
-        self.flat = torch.zeros(n, dtype=torch.float32, device=first.device)
+        if flat is not None and (flat.numel() != n or flat.dtype != torch.float32 or flat.device != first.device):
+            raise ValueError("bucket storage must be a flat fp32 tensor of the parameters' total size on their device")
+        self.flat = flat if flat is not None else torch.zeros(n, dtype=torch.float32, device=first.device)
         self.views: Dict[str, torch.Tensor] = {}
         off = 0
         for k, p in params.items():
@@ -104,7 +159,7 @@ class ShardedMapStep:
     def __init__(self, params: Dict[str, torch.Tensor], frame_fn: Optional[Callable] = None,
                  group: Optional[dist.ProcessGroup] = None, forward_fn: Optional[Callable] = None,
                  streams: int = 1, direct_targets: bool = False, prepare_fn: Optional[Callable] = None,
-                 overwrite_first: bool = False):
+                 overwrite_first: bool = False, exchange: str = "auto"):
         """streams > 1 (forward_fn mode, CUDA only): consecutive keyframes alternate between `streams` CUDA
         streams, so the latency-bound binning kernels of one frame overlap the blend kernels of another.
         direct_targets: forward_fn receives a third argument, a dict of gradient accumulators (views of a flat
@@ -117,7 +172,21 @@ class ShardedMapStep:
         if (frame_fn is None) == (forward_fn is None):
             raise ValueError("give exactly one of frame_fn / forward_fn")
         self.params = params
-        self.bucket = GradBucket(params)
+        # exchange: "nccl" = dist.all_reduce; "peer" / "nvls" = the library's one-kernel exchange over peer memory
+        # (P2P loads/stores / multimem through the switch); "auto" = nvls, else peer, else nccl (CPU / gloo: nccl path).
+        self.peer = None
+        self.exchange_error = None
+        first_ = next(iter(params.values()))
+        if (exchange != "nccl" and first_.is_cuda and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(group) > 1):
+            try:
+                self.peer = PeerExchange(sum(p.numel() for p in params.values()), first_.device, group, exchange)
+            except Exception as ex:   # noqa: BLE001 - any failure of the symmetric-memory plumbing means NCCL
+                if exchange != "auto":
+                    raise
+                self.exchange_error = repr(ex)[:300]
+        self.exchange = self.peer.mode if self.peer is not None else "nccl"
+        self.bucket = GradBucket(params, self.peer.flat if self.peer is not None else None)
         self.frame_fn = frame_fn
         self.forward_fn = forward_fn
         # prepare_fn(params, keyframe) -> handle: enqueues the part of the forward that precedes its host
@@ -251,6 +320,9 @@ class ShardedMapStep:
             losses = [self.frame_fn(self.params, kf) for kf in mine]
         self._mark(1)
         if self.world > 1:
-            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.peer is not None:
+                self.peer.all_reduce()
+            else:
+                dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
         self._mark(2)
         return losses
