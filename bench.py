@@ -657,22 +657,21 @@ def main():
     line["run"]["R_mean"] = sum(R_list) / max(len(R_list), 1)
     line["run"]["visible_mean"] = sum(vis_list) / max(len(vis_list), 1)
 
-    # ---- where a step's time goes on a rank: kernels vs the gradient exchange (CUDA events inside the step) ----
+    # ---- where a step's time goes on a rank: kernels vs the gradient exchange (CUDA events inside the steps, which run
+    # back to back exactly like the timed region; read after the last one) ----
     stepper.timing = True
-    tk, tc = [], []
-    for _ in range(5):
+    for _ in range(12):
         step()
-        tm = stepper.timings()
-        tk.append(tm["kernel_ms"])
-        tc.append(tm["comm_ms"])
-        barrier()
+    tm = stepper.timings()[2:]
     stepper.timing = False
-    t = torch.tensor([statistics.median(tk), statistics.median(tc)], device=device)
+    barrier()
+    t = torch.tensor([statistics.median(x["kernel_ms"] for x in tm), statistics.median(x["comm_ms"] for x in tm)], device=device)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     line["kernel_ms"], line["comm_ms"] = round(float(t[0]), 4), round(float(t[1]), 4)
     line["run"]["timing_note"] = ("kernel_ms: step start -> local gradient bucket complete; comm_ms: the exchange after it "
-                                  "(exposed part of the all-reduce); medians of 5 steps, max over ranks")
+                                  "(includes waiting for the slowest rank); steps back to back as in the timed region, "
+                                  "medians of 10 steps, max over ranks")
 
     # ---- per-stage profile (untimed pass with the library's stage events on) --------------------
     lib = dgr._lib
@@ -735,8 +734,6 @@ def main():
         host_in = {k: gs_cpu[k].contiguous().pin_memory() for k in names}
         host_grad = torch.empty(stepper.bucket.flat.numel(), dtype=torch.float32).pin_memory()
         host_img = torch.empty(my_kfs, 3, args.H, args.W).pin_memory()
-        h2d = sum(t.numel() * 4 for t in host_in.values())
-        d2h = host_grad.numel() * 4 + host_img.numel() * 4
 
         # Pipelined like a real consumer would: every step still uploads its inputs from pinned host memory and
         # downloads its results (gradient bucket + images), but on a copy stream with double-buffered device
@@ -744,10 +741,26 @@ def main():
         copy_stream = torch.cuda.Stream(device)       # uploads
         down_stream = torch.cuda.Stream(device)       # downloads (PCIe is full duplex: keep the directions apart)
         main_stream = torch.cuda.current_stream(device)
-        # one flat pinned host block / one flat device block per buffer: a single copy per direction per step
+        # one flat pinned host block / one flat device block per buffer: a single copy per direction per step.
+        # With N > 1 ranks the host copies are SHARDED: rank r uploads only its 1/N slice of the parameters and the
+        # library's all-gather kernel replicates it over NVLink (include/gscomm_b200.h); after the exchange every rank
+        # holds the reduced bucket and rank r downloads only its 1/N slice — host traffic does not grow with N.
         sizes = [params[k].numel() for k in names]
+        total = sum(sizes)
         host_flat = torch.cat([host_in[k].reshape(-1) for k in names]).pin_memory()
-        pflat = [torch.empty(sum(sizes), dtype=torch.float32, device=device) for _ in range(2)]
+        shard = distributed and stepper.peer is not None
+        if shard:
+            from gsr_mapstep import PeerExchange
+            pex = [PeerExchange(total, device, None, "auto") for _ in range(2)]
+            pflat = [p.flat for p in pex]
+            ulo, uhi = pex[0].slice_range()
+            glo, ghi = stepper.peer.slice_range()
+        else:
+            pex = None
+            pflat = [torch.empty(total, dtype=torch.float32, device=device) for _ in range(2)]
+            ulo, uhi, glo, ghi = 0, total, 0, total
+        h2d = (uhi - ulo) * 4
+        d2h = (ghi - glo) * 4 + host_img.numel() * 4
         pbuf = []
         for fl in pflat:
             d, off = {}, 0
@@ -757,7 +770,7 @@ def main():
             pbuf.append(d)
         up_done = [torch.cuda.Event() for _ in range(2)]
         free_in = [torch.cuda.Event() for _ in range(2)]      # step that read pbuf[b] has finished
-        stage_grad = [torch.empty_like(stepper.bucket.flat) for _ in range(2)]
+        stage_grad = [torch.empty(ghi - glo, dtype=torch.float32, device=device) for _ in range(2)]
         stage_img = [torch.empty(max(my_kfs, 1), 3, args.H, args.W, device=device) for _ in range(2)]
         free_out = [torch.cuda.Event() for _ in range(2)]     # download of stage[b] has finished
         state = {"i": 0}
@@ -765,7 +778,9 @@ def main():
         def upload(b):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free_in[b])
-                pflat[b].copy_(host_flat, non_blocking=True)
+                pflat[b][ulo:uhi].copy_(host_flat[ulo:uhi], non_blocking=True)
+                if shard:
+                    pex[b].all_gather()
                 up_done[b].record(copy_stream)
 
         for b in range(2):
@@ -780,7 +795,7 @@ def main():
             main_stream.wait_event(up_done[b])
             imgs = stepper.step(kfs, params=pbuf[b]) if stepper.direct_targets else step()
             main_stream.wait_event(free_out[b])
-            stage_grad[b].copy_(stepper.bucket.flat, non_blocking=True)
+            stage_grad[b].copy_(stepper.bucket.flat[glo:ghi], non_blocking=True)
             if imgs:
                 torch.stack(imgs, out=stage_img[b][:len(imgs)])
             free_in[b].record(main_stream)
@@ -788,7 +803,7 @@ def main():
             done.record(main_stream)
             with torch.cuda.stream(down_stream):
                 down_stream.wait_event(done)
-                host_grad.copy_(stage_grad[b], non_blocking=True)
+                host_grad[glo:ghi].copy_(stage_grad[b], non_blocking=True)
                 host_img[:len(imgs)].copy_(stage_img[b][:len(imgs)], non_blocking=True)
                 free_out[b].record(down_stream)
             state["i"] = i + 1
@@ -814,10 +829,13 @@ def main():
             ems = float(t.item())
         line["e2e"] = {"value": args.keyframes * n_e2e / (ems / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                       "sharded_host_copies": bool(shard),
                        "what": "every step: Gaussian parameters uploaded from pinned host memory, 8-keyframe step through "
                                "GaussianRasterizer, gradient bucket + rendered images downloaded to pinned host memory; "
                                "copies run on a copy stream with double-buffered device parameters / result staging so "
-                               "they overlap the neighbouring steps' kernels"}
+                               "they overlap the neighbouring steps' kernels.  With N > 1 every rank moves 1/N of the "
+                               "parameters / of the reduced bucket over PCIe (bytes_per_step are per rank) and the "
+                               "library's all-gather replicates the parameters over NVLink"}
 
     extras = rank == 0 and world == 1 and not args.no_extras
     if extras:

@@ -42,6 +42,13 @@ size_t gsr_allreduce_flag_words(void);
 int gsr_allreduce_sum_f32(gsr_stream_t stream, int32_t nranks, int32_t rank, float* const* bucket, float* multicast,
                           uint32_t* const* flags, int64_t n, uint32_t epoch);
 
+/* All-gather over the same kind of symmetric buffer: rank r's slice — floats [r * ceil(n4 / nranks) * 4, ...) with
+ * n4 = ceil(n / 4), the slicing of the all-reduce — is copied from its own buffer into every other rank's (P2P stores, or
+ * one multimem.st per 16 bytes).  Used to replicate the Gaussian parameters when every rank uploads only its 1/nranks
+ * share from host memory.  Same flag / epoch rules (a separate flag array and epoch counter per buffer). */
+int gsr_allgather_f32(gsr_stream_t stream, int32_t nranks, int32_t rank, float* const* buffer, float* multicast,
+                      uint32_t* const* flags, int64_t n, uint32_t epoch);
+
 #ifdef __cplusplus
 }
 #endif

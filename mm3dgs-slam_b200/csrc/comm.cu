@@ -121,6 +121,36 @@ __global__ void __launch_bounds__(kArThreads) k_allreduce(ArArgs a)
     handshake(a, 1);                                  // every rank's stores have landed everywhere
 }
 
+// All-gather: rank r's slice of the buffer (same slicing as the all-reduce) is copied into every other rank's buffer.
+template <int NR, bool NVLS>
+__global__ void __launch_bounds__(kArThreads) k_allgather(ArArgs a)
+{
+    handshake(a, 0);                                  // every rank is done reading the buffer's previous contents
+    const long long n4 = (a.n + 3) >> 2;
+    const long long per = (n4 + NR - 1) / NR;
+    const long long lo = per * a.rank, hi = min(lo + per, n4);
+    const long long stride = (long long)gridDim.x * kArThreads;
+    const float4* mine = reinterpret_cast<const float4*>(a.bucket[a.rank]);
+    for (long long i = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += stride) {
+        const float4 v = mine[i];
+        if (NVLS) {
+            multimem_st4(reinterpret_cast<float4*>(a.multicast) + i, v);
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+                if (r != a.rank) st_peer4(reinterpret_cast<float4*>(a.bucket[r]) + i, v);
+        }
+    }
+    handshake(a, 1);                                  // every rank's slice has landed everywhere
+}
+
+template <int NR>
+static void launch_ag(const ArArgs& a, int blocks, cudaStream_t s)
+{
+    if (a.multicast) k_allgather<NR, true><<<blocks, kArThreads, 0, s>>>(a);
+    else k_allgather<NR, false><<<blocks, kArThreads, 0, s>>>(a);
+}
+
 template <int NR>
 static void launch_ar(const ArArgs& a, int blocks, cudaStream_t s)
 {
@@ -136,8 +166,8 @@ extern "C" {
 
 size_t gsr_allreduce_flag_words(void) { return (size_t)kArFlagWords; }
 
-int gsr_allreduce_sum_f32(gsr_stream_t stream_, int32_t nranks, int32_t rank, float* const* bucket, float* multicast,
-                          uint32_t* const* flags, int64_t n, uint32_t epoch)
+static int exchange(bool gather, gsr_stream_t stream_, int32_t nranks, int32_t rank, float* const* bucket, float* multicast,
+                    uint32_t* const* flags, int64_t n, uint32_t epoch)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nranks < 1 || nranks > GSR_COMM_MAX_RANKS || rank < 0 || rank >= nranks) return api_fail(GSR_ERR_INVALID, "bad rank / nranks");
@@ -155,15 +185,36 @@ int gsr_allreduce_sum_f32(gsr_stream_t stream_, int32_t nranks, int32_t rank, fl
     long long blocks = (per + 2 * kArThreads - 1) / (2 * kArThreads);
     if (blocks > ar_blocks()) blocks = ar_blocks();
     if (blocks < 1) blocks = 1;
-    switch (nranks) {
-        case 2: launch_ar<2>(a, (int)blocks, stream); break;
-        case 4: launch_ar<4>(a, (int)blocks, stream); break;
-        default: launch_ar<8>(a, (int)blocks, stream); break;
+    if (gather) {
+        if (blocks > 32) blocks = 32;       // a copy: few CTAs saturate the links and the rest of the GPU keeps computing
+        switch (nranks) {
+            case 2: launch_ag<2>(a, (int)blocks, stream); break;
+            case 4: launch_ag<4>(a, (int)blocks, stream); break;
+            default: launch_ag<8>(a, (int)blocks, stream); break;
+        }
+    } else {
+        switch (nranks) {
+            case 2: launch_ar<2>(a, (int)blocks, stream); break;
+            case 4: launch_ar<4>(a, (int)blocks, stream); break;
+            default: launch_ar<8>(a, (int)blocks, stream); break;
+        }
     }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return api_fail(GSR_ERR_CUDA, "all-reduce launch", e);
+    if (e != cudaSuccess) return api_fail(GSR_ERR_CUDA, "exchange launch", e);
     api_count_launches(1);
     return GSR_OK;
+}
+
+int gsr_allreduce_sum_f32(gsr_stream_t stream, int32_t nranks, int32_t rank, float* const* bucket, float* multicast,
+                          uint32_t* const* flags, int64_t n, uint32_t epoch)
+{
+    return exchange(false, stream, nranks, rank, bucket, multicast, flags, n, epoch);
+}
+
+int gsr_allgather_f32(gsr_stream_t stream, int32_t nranks, int32_t rank, float* const* buffer, float* multicast,
+                      uint32_t* const* flags, int64_t n, uint32_t epoch)
+{
+    return exchange(true, stream, nranks, rank, buffer, multicast, flags, n, epoch);
 }
 
 }  // extern "C"

@@ -43,6 +43,18 @@ for mode in modes:
             ref = ex.flat.clone()
             dist.broadcast(ref, 0)
             assert torch.equal(ref, ex.flat), (mode, n, rep, "ranks differ")
+            # all-gather: every rank contributes its slice; the result is the concatenation of the owners' slices
+            mine = torch.randn(n, generator=g).to(dev)
+            ex.flat.copy_(mine)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            want = mine.clone()
+            for r in range(world):
+                lo, hi = ex.slice_range(r)
+                want[lo:hi] = parts[r][lo:hi]
+            ex.all_gather()
+            torch.cuda.synchronize()
+            assert torch.equal(ex.flat, want), (mode, n, rep, "all_gather")
         del ex
 if rank == 0:
     print("peer exchange ok:", modes)
