@@ -113,12 +113,6 @@ int gsr_compact_gather(gsr_stream_t stream, int64_t P, int64_t rows_out, int32_t
                        const uint8_t* keep, const uint32_t* new_index, int32_t nbuf, const float* const* src,
                        float* const* dst);
 
-/* dst[i] += src[0][i] + ... + src[nsrc-1][i] over n floats in ONE pass (16-byte aligned buffers; src: HOST array of
- * device pointers).  The keyframe-sharded map step back-propagates consecutive keyframes on different streams into
- * per-stream gradient buckets; this folds them into the main bucket before the exchange. */
-#define GSR_SUM_MAX_SOURCES 7
-int gsr_sum_into(gsr_stream_t stream, float* dst, const float* const* src, int32_t nsrc, int64_t n);
-
 #ifdef __cplusplus
 }
 #endif

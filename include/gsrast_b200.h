@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 5
+#define GSR_ABI_VERSION 6
 
 typedef void* gsr_stream_t; /* cudaStream_t */
 
@@ -59,7 +59,13 @@ typedef struct gsr_gaussians {
     int32_t P;                 /* number of Gaussians */
     int32_t sh_degree;         /* active SH degree D (0..3) */
     int32_t sh_coeffs;         /* M = coefficients per Gaussian in `shs` (0 if absent) */
-    int32_t _pad;
+    int32_t raw_params;        /* 0: opacities / scales / rotations hold the values the rasterizer works with (the
+                                * reference's convention).  1 (extension): they hold the RAW optimizer
+                                * parameters and the library applies the reference's activations itself — opacity =
+                                * sigmoid(x), scale = exp(s), rotation = q / max(|q|, 1e-12) (R/slam/gaussian_model.py:
+                                * 108-132, torch.sigmoid / torch.exp / F.normalize) — and gsr_backward returns the
+                                * gradients w.r.t. the raw parameters (dL_dopacity_raw, dL_dscales, dL_drotations).
+                                * Requires scales + rotations (not cov3D_precomp). */
     const float* means3D;      /* [P,3] */
     const float* shs;          /* [P,M,3] or NULL */
     const float* colors_precomp; /* [P,3] or NULL (exactly one of shs / colors_precomp) */
@@ -117,6 +123,8 @@ typedef struct gsr_grads {
     int32_t _pad;
     float* dL_dextra;      /* [P,3] (acc) gradient w.r.t. the extra colours; required iff extra colours are used
                             * (with extra_mode 1 it is scratch: the chain to the means is applied in the library) */
+    float* dL_dopacity_raw; /* [P] required iff raw_params: gradient w.r.t. the raw opacity (written, or added with
+                             * `accumulate`); dL_dopacity is then scratch for the blend backward (acc) */
 } gsr_grads;
 
 int gsr_abi_version(void);

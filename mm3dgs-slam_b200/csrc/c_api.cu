@@ -183,6 +183,8 @@ static int check_common(const gsr_gaussians* g, const gsr_camera* cam)
             return fail(GSR_ERR_INVALID, "camera pointers required");
         if (g->extra_mode != 0 && (g->extra_mode != 1 || g->extra_colors))
             return fail(GSR_ERR_INVALID, "extra_mode must be 0, or 1 with extra_colors == NULL");
+        if (g->raw_params != 0 && (g->raw_params != 1 || !sr))
+            return fail(GSR_ERR_INVALID, "raw_params must be 0, or 1 with scales + rotations");
     }
     return GSR_OK;
 }
@@ -267,6 +269,7 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     PreArgs a;
     a.P = P; a.D = g->sh_degree; a.M = g->shs ? g->sh_coeffs : 0; a.W = W; a.H = H;
     a.gx = (W + kTile - 1) / kTile; a.gy = (H + kTile - 1) / kTile; a.prefiltered = cam->prefiltered;
+    a.raw = g->raw_params;
     a.means = g->means3D; a.scales = g->scales; a.rots = g->rotations; a.opac = g->opacities; a.shs = g->shs;
     a.colors = g->colors_precomp; a.cov3D_pre = g->cov3D_precomp;
     a.view = cam->viewmatrix; a.proj = cam->projmatrix; a.campos = cam->campos;
@@ -366,6 +369,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     const int M = g->shs ? g->sh_coeffs : 0;
     if ((M > 0 && !gr->dL_dsh) || (g->scales && (!gr->dL_dscales || !gr->dL_drotations)))
         return fail(GSR_ERR_INVALID, "gradient buffer for a provided input missing");
+    if (g->raw_params && !gr->dL_dopacity_raw) return fail(GSR_ERR_INVALID, "dL_dopacity_raw required with raw_params");
     GeomWS gw = geom_ws_carve((char*)geom_ws, P, W, H);
     ImgWS iw = img_ws_carve((char*)img_ws, W, H);
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
@@ -382,6 +386,7 @@ int gsr_backward(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_camera*
     }
     PreBwdArgs a;
     a.P = P; a.D = g->sh_degree; a.M = M; a.W = W; a.H = H;
+    a.raw = g->raw_params; a.opac = g->opacities; a.dL_dopacity = gr->dL_dopacity; a.dL_dopacity_raw = gr->dL_dopacity_raw;
     a.means = g->means3D; a.scales = g->scales; a.rots = g->rotations; a.shs = g->shs; a.cov3D_pre = g->cov3D_precomp;
     a.view = cam->viewmatrix; a.proj = cam->projmatrix; a.campos = cam->campos;
     a.scale_mod = g->scale_modifier; a.tanfovx = cam->tanfovx; a.tanfovy = cam->tanfovy;

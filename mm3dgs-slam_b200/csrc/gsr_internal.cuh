@@ -74,6 +74,7 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
 // ---- launchers (each enqueues on `s`) ---------------------------------------------------------
 struct PreArgs {
     int P, D, M, W, H, gx, gy, prefiltered;
+    int raw;                  // opacities / scales / rotations are raw optimizer parameters (fused activations)
     const float *means, *scales, *rots, *opac, *shs, *colors, *cov3D_pre, *view, *proj, *campos;
     float scale_mod, tanfovx, tanfovy, focal_x, focal_y;
     int* radii;
@@ -111,6 +112,10 @@ void launch_blend_stats(int W, int H, int gx, int gy, const uint2* ranges, const
 
 struct PreBwdArgs {
     int P, D, M, W, H;
+    int raw;                      // see PreArgs::raw: gradients are chained back to the raw parameters
+    const float* opac;            // [P] raw opacities (raw mode)
+    const float* dL_dopacity;     // [P] dL/d(activated opacity) accumulated by the blend backward (raw mode)
+    float* dL_dopacity_raw;       // [P] out: dL/d(raw opacity) (raw mode)
     const float *means, *scales, *rots, *shs, *cov3D_pre, *view, *proj, *campos;
     float scale_mod, tanfovx, tanfovy, focal_x, focal_y;
     const int* radii;

@@ -113,59 +113,11 @@ __global__ void __launch_bounds__(256) k_compact_gather(CompactArgs a, const uin
     }
 }
 
-// dst += src[0] + ... + src[nsrc-1] in one pass (the per-stream gradient buckets of the map step folded into the main one)
-struct SumArgs { const float* src[GSR_SUM_MAX_SOURCES]; int nsrc; };
-__global__ void __launch_bounds__(256) k_sum_into(float* __restrict__ dst, SumArgs a, long long n)
-{
-    const long long n4 = n >> 2;
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 acc = d4[i];
-#pragma unroll
-        for (int k = 0; k < GSR_SUM_MAX_SOURCES; k++)
-            if (k < a.nsrc) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(a.src[k]) + i);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-        d4[i] = acc;
-    }
-    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float acc = dst[i];
-        for (int k = 0; k < a.nsrc; k++) acc += a.src[k][i];
-        dst[i] = acc;
-    }
-}
-
 }  // namespace gsr
 
 using namespace gsr;
 
 extern "C" {
-
-int gsr_sum_into(gsr_stream_t stream_, float* dst, const float* const* src, int32_t nsrc, int64_t n)
-{
-    if (n < 0 || nsrc < 0 || nsrc > GSR_SUM_MAX_SOURCES) return api_fail(GSR_ERR_INVALID, "bad size");
-    if (n == 0 || nsrc == 0) return GSR_OK;
-    if (!dst || !src) return api_fail(GSR_ERR_INVALID, "null argument");
-    SumArgs a;
-    a.nsrc = nsrc;
-    uintptr_t al = (uintptr_t)dst;
-    for (int k = 0; k < GSR_SUM_MAX_SOURCES; k++) {
-        a.src[k] = k < nsrc ? src[k] : nullptr;
-        if (k < nsrc && !src[k]) return api_fail(GSR_ERR_INVALID, "null source");
-        if (k < nsrc) al |= (uintptr_t)src[k];
-    }
-    if (al & 15) return api_fail(GSR_ERR_INVALID, "buffers must be 16-byte aligned");
-    long long blocks = ((n >> 2) + 255) / 256;
-    const long long cap = (long long)device_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    k_sum_into<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(dst, a, (long long)n);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return api_fail(GSR_ERR_CUDA, "sum launch", e);
-    api_count_launches(1);
-    return GSR_OK;
-}
 
 size_t gsr_compact_ws_bytes(int64_t P)
 {

@@ -119,6 +119,18 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
         const int idx = base + tid;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
         uint32_t dkey = 0xffffffffu;   // depth key of a visible Gaussian
+        if (a.raw && tid < nb) {
+            // fused activations (gsr_gaussians.raw_params): exp / normalize / sigmoid applied to this thread's staged
+            // parameters IN PLACE in shared memory, so the code below — whose floating-point association order is
+            // pinned bit for bit against the reference — is the same instruction stream for both kinds of input
+            float inv_norm;
+            const V3 sc = act_exp3(V3{in.scales[3 * tid], in.scales[3 * tid + 1], in.scales[3 * tid + 2]});
+            const V4 q = act_normalize4(V4{in.rots[4 * tid], in.rots[4 * tid + 1], in.rots[4 * tid + 2], in.rots[4 * tid + 3]},
+                                        inv_norm);
+            in.scales[3 * tid] = sc.x; in.scales[3 * tid + 1] = sc.y; in.scales[3 * tid + 2] = sc.z;
+            in.rots[4 * tid] = q.x; in.rots[4 * tid + 1] = q.y; in.rots[4 * tid + 2] = q.z; in.rots[4 * tid + 3] = q.w;
+            in.opac[tid] = act_sigmoid(in.opac[tid]);
+        }
         if (tid < nb) {
             const float* view = s_cam;
             const float* proj = s_cam + 16;

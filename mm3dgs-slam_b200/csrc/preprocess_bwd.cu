@@ -148,10 +148,22 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
             const Sym2 H = cov2d_grad_from_conic(r1.x, r1.y, r1.z, in.gc[4 * tid], in.gc[4 * tid + 1], in.gc[4 * tid + 3]);
             V3 dM0, dM1;
             if (has_sr) {
-                const V3 s_eff = {a.scale_mod * in.scales[3 * tid], a.scale_mod * in.scales[3 * tid + 1],
-                                  a.scale_mod * in.scales[3 * tid + 2]};
-                const V4 q = {in.rots[4 * tid], in.rots[4 * tid + 1], in.rots[4 * tid + 2], in.rots[4 * tid + 3]};
+                V3 sc = {in.scales[3 * tid], in.scales[3 * tid + 1], in.scales[3 * tid + 2]};
+                V4 q = {in.rots[4 * tid], in.rots[4 * tid + 1], in.rots[4 * tid + 2], in.rots[4 * tid + 3]};
+                float inv_norm = 1.f;
+                if (a.raw) {
+                    sc = act_exp3(sc);
+                    q = act_normalize4(q, inv_norm);
+                }
+                const V3 s_eff = {a.scale_mod * sc.x, a.scale_mod * sc.y, a.scale_mod * sc.z};
                 cov_chain_scale_rot(f, H, s_eff, q, dscale, dq, dM0, dM1);
+                if (a.raw) {
+                    // s = exp(r): ds/dr = s;  q = r / |r|: dq/dr = (I - q q^T) / |r|
+                    dscale.x *= sc.x; dscale.y *= sc.y; dscale.z *= sc.z;
+                    const float qd = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w;
+                    dq.x = (dq.x - q.x * qd) * inv_norm; dq.y = (dq.y - q.y * qd) * inv_norm;
+                    dq.z = (dq.z - q.z * qd) * inv_norm; dq.w = (dq.w - q.w * qd) * inv_norm;
+                }
             } else {
                 float cov6[6];
 #pragma unroll
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
                         float* o = a.dL_dsh + (size_t)idx * a.M * 3;
 #pragma unroll
                         for (int ch = 0; ch < 3; ch++) {
-                            if (ACC) o[ch] += GSR_SH_C0 * dRGB[ch];
+                            if (ACC) atomicAdd(&o[ch], GSR_SH_C0 * dRGB[ch]);
                             else o[ch] = GSR_SH_C0 * dRGB[ch];
                         }
                         if (!ACC)
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
                     const V3 ddir = sh_grad(a.D, sh, dir, dRGB, tmp);
                     float* o = a.dL_dsh + (size_t)idx * a.M * 3;
                     for (int k = 0; k < used; k++) {
-                        if (ACC) o[k] += tmp[k];
+                        if (ACC) atomicAdd(&o[k], tmp[k]);
                         else o[k] = tmp[k];
                     }
                     if (!ACC)
@@ -239,9 +251,15 @@ __global__ void __launch_bounds__(kPB, 2) k_preprocess_bwd(PreBwdArgs a, int nch
         if (a.dL_dcov3D != nullptr && tid < nb) {
 #pragma unroll
             for (int k = 0; k < 6; k++) {
-                if (ACC) a.dL_dcov3D[(size_t)idx * 6 + k] += dcov[k];
+                if (ACC) atomicAdd(&a.dL_dcov3D[(size_t)idx * 6 + k], dcov[k]);
                 else a.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
             }
+        }
+        if (a.raw && tid < nb) {   // o = sigmoid(x): do/dx = o (1 - o); culled Gaussians received no opacity gradient
+            const float o = act_sigmoid(a.opac[idx]);
+            const float g = a.dL_dopacity[idx] * o * (1.f - o);
+            if (ACC) atomicAdd(&a.dL_dopacity_raw[idx], g);
+            else a.dL_dopacity_raw[idx] = g;
         }
 
         // the bulk stores issued two iterations ago have finished reading this output stage

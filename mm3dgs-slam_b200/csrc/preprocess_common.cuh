@@ -37,8 +37,9 @@ __device__ __forceinline__ void stage_in(const float* __restrict__ src, float* d
         for (int i = tid; i < n; i += kPB) dst[i] = ld_stream1(src + i);
     }
 }
-// Copy n contiguous floats shared -> global (ACC: add to what is there).  Only the ragged / unaligned chunks take
-// this path; full aligned chunks leave through the TMA unit (async_copy.cuh).
+// Copy n contiguous floats shared -> global (ACC: add to what is there — with float atomics, like the TMA reduce-adds
+// of the full chunks, so that frames back-propagated on different streams may share one accumulator).  Only the
+// ragged / unaligned chunks take this path; full aligned chunks leave through the TMA unit (async_copy.cuh).
 template <bool ACC>
 __device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int n, int tid)
 {
@@ -49,8 +50,22 @@ __device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* 
         for (int i = tid; i < n4; i += kPB) d4[i] = s4[i];
         for (int i = (n4 << 2) + tid; i < n; i += kPB) dst[i] = src[i];
     } else {
-        for (int i = tid; i < n; i += kPB) dst[i] = ACC ? dst[i] + src[i] : src[i];
+        for (int i = tid; i < n; i += kPB) {
+            if (ACC) atomicAdd(dst + i, src[i]);
+            else dst[i] = src[i];
+        }
     }
+}
+
+// Raw optimizer parameters -> the values the rasterizer works with (gsr_gaussians.raw_params): the reference applies
+// torch.exp / torch.sigmoid / F.normalize(eps=1e-12) to its parameters on every render (R/slam/gaussian_model.py:108-132).
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ V3 act_exp3(const V3& s) { return V3{expf(s.x), expf(s.y), expf(s.z)}; }
+__device__ __forceinline__ V4 act_normalize4(const V4& q, float& inv_norm)
+{
+    const float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    inv_norm = 1.0f / fmaxf(n, 1e-12f);
+    return V4{q.x * inv_norm, q.y * inv_norm, q.z * inv_norm, q.w * inv_norm};
 }
 
 }  // namespace gsr

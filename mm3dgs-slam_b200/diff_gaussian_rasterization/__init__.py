@@ -45,7 +45,7 @@ _LIB_PATH = os.environ.get(
 
 class _Gaussians(ctypes.Structure):
     _fields_ = [
-        ("P", ctypes.c_int32), ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32), ("_pad", ctypes.c_int32),
+        ("P", ctypes.c_int32), ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32), ("raw_params", ctypes.c_int32),
         ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p),
         ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
         ("cov3D_precomp", ctypes.c_void_p), ("scale_modifier", ctypes.c_float), ("extra_mode", ctypes.c_int32),
@@ -65,7 +65,8 @@ class _Grads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "dL_dmeans2D", "dL_dconic", "dL_dopacity", "dL_dcolors", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
         "dL_dscales", "dL_drotations", "dL_dviewmatrix", "dL_dprojmatrix", "dL_dcampos")] + [
-        ("accumulate", ctypes.c_int32), ("_pad", ctypes.c_int32), ("dL_dextra", ctypes.c_void_p)]
+        ("accumulate", ctypes.c_int32), ("_pad", ctypes.c_int32), ("dL_dextra", ctypes.c_void_p),
+        ("dL_dopacity_raw", ctypes.c_void_p)]
 
 
 def _load():
@@ -94,7 +95,7 @@ def _load():
                                  ctypes.POINTER(_Grads)]
     lib.gsr_mark_visible.restype = ctypes.c_int
     lib.gsr_mark_visible.argtypes = [vp, i32, vp, vp, vp, vp]
-    if lib.gsr_abi_version() != 5:
+    if lib.gsr_abi_version() != 6:
         raise ImportError("libgsrast_b200.so ABI version mismatch")
     return lib
 
@@ -143,12 +144,12 @@ DEPTH_SILHOUETTE = "depth_silhouette"   # extra_colors=DEPTH_SILHOUETTE: (z, 1, 
 
 
 def _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
-             extra=None):
-    """extra: None, a [P,3] tensor, or DEPTH_SILHOUETTE."""
+             extra=None, raw=False):
+    """extra: None, a [P,3] tensor, or DEPTH_SILHOUETTE.  raw: opacities / scales / rotations are raw parameters."""
     P = means3D.shape[0]
     M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
     gen = isinstance(extra, str)
-    g = _Gaussians(P, int(rs.sh_degree), M, 0, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
+    g = _Gaussians(P, int(rs.sh_degree), M, 1 if raw else 0, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
                    _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp), float(rs.scale_modifier), 1 if gen else 0,
                    None if gen else _ptr(extra))
     c = _Camera(int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy), _ptr(view), _ptr(proj),
@@ -217,7 +218,7 @@ def _extra_key(extra):
 
 class PreparedFrame:
     """Phase 1 of a forward (projection + depth sort) already enqueued; see prepare_forward()."""
-    __slots__ = ("tensors", "rs", "radii", "geom", "img", "r_host", "event", "stream", "g", "c", "key")
+    __slots__ = ("tensors", "rs", "radii", "geom", "img", "r_host", "event", "stream", "g", "c", "key", "raw")
 
     def release(self):
         if getattr(self, "r_host", None) is not None:
@@ -242,7 +243,7 @@ def _enqueue_r_copy(geom, P, W, H, stream):
 
 
 def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precomp=None, scales=None, rotations=None,
-                    cov3D_precomp=None, extra_colors=None):
+                    cov3D_precomp=None, extra_colors=None, raw_params=False):
     """Extension.  Enqueue phase 1 of a forward (projection, tile rectangles, instance count R, depth sort)
     without waiting for R, and return a handle to pass as `prepared=` to GaussianRasterizer.forward with the
     SAME tensors and settings.  Issuing phase 1 of several frames before the first forward() means every
@@ -266,6 +267,7 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
         pf = PreparedFrame()
         pf.tensors, pf.rs = tuple(t) + (extra,), rs
         pf.key = _input_key(t, extra)
+        pf.raw = bool(raw_params)
         pf.stream = torch.cuda.current_stream(dev)
         pf.radii = torch.empty((P,), dtype=torch.int32, device=dev)
         pf.r_host = None
@@ -276,7 +278,8 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
         pf.geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
         pf.img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
         pf.g, pf.c = _structs(*t[:7], rs, *t[7:11],
-                              extra if (isinstance(extra, str) or (extra is not None and extra.numel())) else None)
+                              extra if (isinstance(extra, str) or (extra is not None and extra.numel())) else None,
+                              raw=pf.raw)
         _check(_lib.gsr_forward_preprocess(pf.stream.cuda_stream, ctypes.byref(pf.g), ctypes.byref(pf.c),
                                            pf.radii.data_ptr(), pf.geom.data_ptr(), pf.geom.numel(), pf.img.data_ptr(),
                                            pf.img.numel(), None))
@@ -285,7 +288,7 @@ def prepare_forward(means3D, opacities, raster_settings, shs=None, colors_precom
 
 
 def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
-                    extra=None, prepared=None):
+                    extra=None, prepared=None, raw=False):
     """Returns (R, color, radii, geom, binning, img); with `extra` ([P,3] colours) the 7th element is the
     extra [3,H,W] image blended in the same pass.  R is a _Count: the true instance count, with the capacity the
     binning workspace was carved with (what gsr_backward needs) in R.cap.
@@ -313,7 +316,7 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
     if prepared is not None:
         key = _input_key((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, view, proj, campos,
                           bg), extra)
-        if prepared.key != key or prepared.radii.shape[0] != P or prepared.rs is not rs:
+        if prepared.key != key or prepared.radii.shape[0] != P or prepared.rs is not rs or prepared.raw != bool(raw):
             raise RuntimeError("gsrast_b200: `prepared` was made for different inputs / settings")
         radii, geom, img, g, c = prepared.radii, prepared.geom, prepared.img, prepared.g, prepared.c
         if cur != prepared.stream:
@@ -327,7 +330,7 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
         geom = torch.empty(_lib.gsr_geom_ws_bytes(P, W, H), **u8)
         img = torch.empty(_lib.gsr_img_ws_bytes(W, H), **u8)
         g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos,
-                        bg, extra if has_extra else None)
+                        bg, extra if has_extra else None, raw=raw)
         _check(_lib.gsr_forward_preprocess(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), geom.data_ptr(),
                                            geom.numel(), img.data_ptr(), img.numel(), None))
         slot, event = _enqueue_r_copy(geom, P, W, H, cur)
@@ -365,7 +368,7 @@ def _forward_native(means3D, sh, colors_precomp, opacities, scales, rotations, c
 
 def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view,
                      proj, campos, bg, radii, R, geom, binning, img, want_cam, targets=None, extra=None,
-                     grad_extra_img=None):
+                     grad_extra_img=None, raw=False):
     """targets: optional dict of gradient accumulators (means3D, shs, opacities, scales, rotations) the
     kernels add into directly (gsr_grads.accumulate)."""
     dev = means3D.device
@@ -375,18 +378,25 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
     has_sr = scales is not None and scales.numel() != 0
     has_cov = cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0
     # accumulated-into buffers share one zero fill: [means2D 3 | conic 4 | colors 3 | opacity 1] per Gaussian
-    acc = torch.zeros(P * (10 if targets else 11), **f32)
+    # (raw parameters: the blend backward's opacity sums are scratch — the chain through the sigmoid is applied by the
+    #  per-Gaussian backward, which writes / adds dL/d(raw opacity))
+    acc = torch.zeros(P * (10 if (targets and not raw) else 11), **f32)
     g_means2D = acc[: 3 * P].view(P, 3)
     g_conic = acc[3 * P: 7 * P].view(P, 4)
     g_colors = acc[7 * P: 10 * P].view(P, 3)
+    g_opacity_raw = None
     if targets:
         g_opacity, g_means3D = targets["opacities"], targets["means3D"]   # atomics / += land in the accumulators
+        if raw:
+            g_opacity_raw, g_opacity = targets["opacities"], acc[10 * P: 11 * P].view(P, 1)
         g_sh = targets["shs"] if M > 0 else None
         g_scales = targets["scales"] if has_sr else None
         g_rots = targets["rotations"] if has_sr else None
         g_cov3D = None
     else:
         g_opacity = acc[10 * P: 11 * P].view(P, 1)
+        if raw:
+            g_opacity_raw = torch.empty((P, 1), **f32)
         g_means3D = torch.empty((P, 3), **f32)
         g_cov3D = torch.empty((P, 6), **f32) if has_cov else None
         g_sh = torch.empty((P, M, 3), **f32) if M > 0 else None
@@ -396,27 +406,29 @@ def _backward_native(grad_color, means3D, sh, colors_precomp, opacities, scales,
     has_extra = isinstance(extra, str) or (extra is not None and extra.numel() != 0)
     g_extra = torch.zeros((P, 3), **f32) if has_extra else None
     if P == 0:
-        return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra
+        return (g_means2D, g_colors, g_opacity_raw if raw else g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam,
+                g_extra)
     stream = torch.cuda.current_stream(dev).cuda_stream
     g, c = _structs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj, campos, bg,
-                    extra if has_extra else None)
+                    extra if has_extra else None, raw=raw)
     gr = _Grads(g_means2D.data_ptr(), g_conic.data_ptr(), g_opacity.data_ptr(), g_colors.data_ptr(),
                 g_means3D.data_ptr(), _ptr(g_cov3D), _ptr(g_sh), _ptr(g_scales), _ptr(g_rots),
                 g_cam.data_ptr() if want_cam else None,
                 g_cam.data_ptr() + 64 if want_cam else None,
                 g_cam.data_ptr() + 128 if want_cam else None,
-                1 if (targets and not targets.get("_overwrite")) else 0, 0, _ptr(g_extra))
+                1 if (targets and not targets.get("_overwrite")) else 0, 0, _ptr(g_extra), _ptr(g_opacity_raw))
     _check(_lib.gsr_backward(stream, ctypes.byref(g), ctypes.byref(c), radii.data_ptr(), R, _ptr(geom), _ptr(binning),
                              _ptr(img), grad_color.data_ptr(), _ptr(grad_extra_img) if has_extra else None,
                              ctypes.byref(gr)))
-    return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam, g_extra
+    return (g_means2D, g_colors, g_opacity_raw if raw else g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rots, g_cam,
+            g_extra)
 
 
 # ------------------------------------------------------------------------------------------------
 # Public API (same names and argument meaning as the reference)
 # ------------------------------------------------------------------------------------------------
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, grad_targets=None, extra_colors=None, prepared=None):
+                        raster_settings, grad_targets=None, extra_colors=None, prepared=None, raw_params=False):
     """`grad_targets` (extension, optional): dict with fp32 contiguous accumulators for means3D, shs,
     opacities, scales, rotations.  The backward kernels then ADD this call's gradients straight into them
     (e.g. views of the map step's flat bucket) and autograd receives no gradient for those inputs — for
@@ -426,7 +438,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     rs = raster_settings
     out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                     cov3Ds_precomp, rs, rs.viewmatrix, rs.projmatrix, rs.campos, grad_targets,
-                                    extra_colors, prepared)
+                                    extra_colors, prepared, bool(raw_params))
     # reference contract: (color, radii); with extra_colors: (color, extra_image, radii)
     return (out[0], out[1]) if extra_colors is None else (out[0], out[2], out[1])
 
@@ -434,8 +446,12 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None, extra_colors=None, prepared=None):
+                raster_settings, viewmatrix, projmatrix, campos, grad_targets=None, extra_colors=None, prepared=None,
+                raw_params=False):
         rs = raster_settings
+        if raw_params and (scales is None or scales.numel() == 0 or rotations is None or rotations.numel() == 0):
+            raise ValueError("raw_params needs scales and rotations (not cov3D_precomp)")
+        ctx.raw = bool(raw_params)
         if grad_targets:
             if cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0:
                 raise ValueError("grad_targets is not supported with cov3D_precomp")
@@ -455,7 +471,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                                          viewmatrix, projmatrix, campos, rs.bg)]
             means3D_, sh_, colors_, opac_, scales_, rots_, cov_, view_, proj_, campos_, bg_ = t
             extra_ = extra_colors if isinstance(extra_colors, str) else _prep(extra_colors, dev)
-            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_, prepared)
+            args = (means3D_, sh_, colors_, opac_, scales_, rots_, cov_, rs, view_, proj_, campos_, bg_, extra_, prepared,
+                    ctx.raw)
             if rs.debug:
                 try:
                     out = _forward_native(*args)
@@ -495,7 +512,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_extra = _prep(grad_out_extra, dev) if grad_out_extra is not None else torch.zeros_like(grad)
             args = (grad, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, view, proj,
                     campos, bg, radii, ctx.num_rendered, geom, binning, img, want_cam, ctx.grad_targets,
-                    (DEPTH_SILHOUETTE if ctx.extra_gen else extra) if ctx.has_extra else None, grad_extra)
+                    (DEPTH_SILHOUETTE if ctx.extra_gen else extra) if ctx.has_extra else None, grad_extra, ctx.raw)
             if rs.debug:
                 try:
                     res = _backward_native(*args)
@@ -516,11 +533,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_campos = g_cam[32:35].view_as(campos) if ctx.needs_input_grad[11] else None
         if ctx.grad_targets:   # already added into the accumulators by the kernels
             return (None, g_means2D, None, g_colors if has_colors else None, None, None, None, None,
-                    None, g_view, g_proj, g_campos, None, g_extra, None)
+                    None, g_view, g_proj, g_campos, None, g_extra, None, None)
         if opacities.dim() == 1:
             g_opacity = g_opacity.view(-1)
         return (g_means3D, g_means2D, g_sh, g_colors if has_colors else None, g_opacity, g_scales, g_rots, g_cov3D,
-                None, g_view, g_proj, g_campos, None, g_extra, None)
+                None, g_view, g_proj, g_campos, None, g_extra, None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -561,12 +578,16 @@ class GaussianRasterizer(nn.Module):
             return present.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, grad_targets=None, extra_colors=None, prepared=None):
+                cov3D_precomp=None, grad_targets=None, extra_colors=None, prepared=None, raw_params=False):
         """Reference signature and return value (color[3,H,W], radii[P]).  Extensions (keyword-only in spirit):
         `extra_colors` [P,3] -> returns (color, extra_image[3,H,W], radii): the extra colours are blended in the
         same pass (the SLAM renderer's second, depth/silhouette call fused into the first); pass
         extra_colors=DEPTH_SILHOUETTE to have the library generate (z, 1, z^2) from the view-space depth itself;
-        `grad_targets`: see rasterize_gaussians; `prepared`: handle from prepare_forward()."""
+        `grad_targets`: see rasterize_gaussians; `prepared`: handle from prepare_forward();
+        `raw_params=True`: opacities / scales / rotations are the model's RAW parameters (_opacity, _scaling,
+        _rotation) — the library applies sigmoid / exp / normalize itself (R/slam/gaussian_model.py:108-132) and the
+        gradients come back w.r.t. the raw parameters, so the three activation ops and their autograd graph drop out
+        of every render."""
         rs = self.raster_settings
         if (shs is None) == (colors_precomp is None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
@@ -582,4 +603,4 @@ class GaussianRasterizer(nn.Module):
             empty if scales is None else scales,
             empty if rotations is None else rotations,
             empty if cov3D_precomp is None else cov3D_precomp,
-            rs, grad_targets, extra_colors, prepared)
+            rs, grad_targets, extra_colors, prepared, raw_params)

@@ -181,13 +181,13 @@ class ShardedMapStep:
                  overwrite_first: bool = False, exchange: str = "auto"):
         """streams > 1 (forward_fn mode, CUDA only): consecutive keyframes alternate between `streams` CUDA
         streams, so the latency-bound binning kernels of one frame overlap the blend kernels of another.
-        direct_targets: forward_fn receives a third argument, a dict of gradient accumulators (views of a flat
-        bucket, one bucket per stream) for kernels that add their gradients in place; the per-stream buckets
-        are summed into the main one before the all-reduce.
-        overwrite_first (needs direct_targets, and a forward_fn that hands `targets` to the rasterizer's
-        grad_targets unchanged): the first frame written into each bucket in a step carries
-        targets["_overwrite"] = True, so the bucket needs no zero fill (only its opacity slice, which the blend
-        backward adds into) and that frame's gradients are stored instead of read-modify-written."""
+        direct_targets: forward_fn receives a third argument, a dict of gradient accumulators (views of THE flat
+        bucket) for kernels that add their gradients in place.  Every stream adds into the same bucket: the library's
+        backward kernels accumulate with TMA reduce-adds / float atomics, so concurrent frames do not race.
+        overwrite_first (needs direct_targets, ONE stream, and a forward_fn that hands `targets` to the rasterizer's
+        grad_targets unchanged): the first frame of a step carries targets["_overwrite"] = True, so the bucket needs no
+        zero fill (only its opacity slice, which the blend backward adds into) and that frame's gradients are stored
+        instead of added.  (A rank that owns a single keyframe always works this way.)"""
         if (frame_fn is None) == (forward_fn is None):
             raise ValueError("give exactly one of frame_fn / forward_fn")
         self.params = params
@@ -214,21 +214,13 @@ class ShardedMapStep:
         self.prepare_fn = prepare_fn
         self.group = group
         self.direct_targets = direct_targets
-        self.overwrite_first = bool(overwrite_first and direct_targets)
-        self.single_frame_overwrite = True    # see _step
-        self._single = False
         first = next(iter(params.values()))
         self.nstreams = max(1, int(streams)) if (forward_fn is not None and first.is_cuda) else 1
+        # (with several streams an overwriting frame would race with the frames adding on the other streams)
+        self.overwrite_first = bool(overwrite_first and direct_targets and self.nstreams == 1)
+        self.single_frame_overwrite = True    # see _step
+        self._single = False
         self.streams = [torch.cuda.Stream(first.device) for _ in range(self.nstreams)] if self.nstreams > 1 else []
-        # stream i > 0 adds into its own flat buffer (same layout) so concurrent in-place adds never collide
-        self.aux_flat = [torch.zeros_like(self.bucket.flat) for _ in range(self.nstreams - 1)] if direct_targets else []
-        self.aux_views = []
-        for flat in self.aux_flat:
-            views, off = {}, 0
-            for k, p in params.items():
-                views[k] = flat[off: off + p.numel()].view_as(p)
-                off += p.numel()
-            self.aux_views.append(views)
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
@@ -261,7 +253,7 @@ class ShardedMapStep:
         kernels may overwrite (only the opacity slice, which the blend backward adds into, was zeroed)."""
         if not self.direct_targets:
             return None
-        views = self.bucket.views if i == 0 else self.aux_views[i - 1]
+        views = self.bucket.views
         return dict(views, _overwrite=True) if (first and (self.overwrite_first or self._single)) else views
 
     def _call_forward(self, kf, i, handle, first=False):
@@ -276,13 +268,6 @@ class ShardedMapStep:
             handles = [self.prepare_fn(self.params, kf) for kf in mine] if self.prepare_fn else [None] * len(mine)
             return [self._call_forward(kf, 0, h, first=(j == 0)) for j, (kf, h) in enumerate(zip(mine, handles))]
         main = torch.cuda.current_stream()
-        used = max(0, min(n, len(mine)) - 1)
-        if self.overwrite_first or self._single:
-            for views in self.aux_views[:used]:
-                views["opacities"].zero_()      # the rest of a used per-stream bucket is overwritten by its first frame
-        else:
-            for flat in self.aux_flat[:used]:
-                flat.zero_()
         for st in self.streams:
             st.wait_stream(main)
         handles = [None] * len(mine)
@@ -293,28 +278,8 @@ class ShardedMapStep:
         outs = []
         for j, kf in enumerate(mine):
             with torch.cuda.stream(self.streams[j % n]):
-                outs.append(self._call_forward(kf, j % n, handles[j], first=(j < n)))
+                outs.append(self._call_forward(kf, j % n, handles[j], first=(j == 0)))
         return outs
-
-    def _fold(self, aux):
-        """main bucket += the per-stream buckets, one pass (gsr_sum_into); plain adds on CPU tensors (gloo tests)."""
-        if not aux:
-            return
-        main = self.bucket.flat
-        if not main.is_cuda or len(aux) > 7:
-            for flat in aux:
-                main.add_(flat)
-            return
-        import ctypes
-
-        from diff_gaussian_rasterization import _lib
-        _lib.gsr_sum_into.restype = ctypes.c_int
-        _lib.gsr_sum_into.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32,
-                                      ctypes.c_int64]
-        srcs = (ctypes.c_void_p * len(aux))(*[t.data_ptr() for t in aux])
-        rc = _lib.gsr_sum_into(torch.cuda.current_stream(main.device).cuda_stream, main.data_ptr(), srcs, len(aux), main.numel())
-        if rc != 0:
-            raise RuntimeError("gsrast_b200: " + _lib.gsr_last_error().decode())
 
     def my_keyframes(self, keyframes: Sequence):
         return [keyframes[i] for i in shard_keyframes(len(keyframes), self.rank, self.world)]
@@ -341,11 +306,10 @@ class ShardedMapStep:
         else:
             self._marks = None
         self._mark(0)
-        # one frame per bucket (this rank has no more keyframes than streams): every bucket has exactly one writer, so
-        # its kernels may overwrite instead of add — no 56 B/Gaussian zero fill, no read-modify-write — and the order
-        # of the backward calls does not matter
-        self._single = bool(self.direct_targets and self.forward_fn is not None and mine
-                            and len(mine) <= self.nstreams and self.single_frame_overwrite)
+        # this rank owns ONE keyframe (K keyframes on K GPUs): the bucket has exactly one writer, so its kernels may
+        # overwrite instead of add — no 56 B/Gaussian zero fill, no read-modify-write
+        self._single = bool(self.direct_targets and self.forward_fn is not None and len(mine) == 1
+                            and self.single_frame_overwrite)
         if (self.overwrite_first or self._single) and self.forward_fn is not None and mine:
             self.bucket.views["opacities"].zero_()
         else:
@@ -367,7 +331,6 @@ class ShardedMapStep:
                     main.wait_stream(st)
                 for o, _ in outs:
                     o.record_stream(main)
-            self._fold(self.aux_flat[: max(0, min(self.nstreams, len(mine)) - 1)])   # only the streams used
             losses = [o.detach() for o, _ in outs]
         else:
             losses = [self.frame_fn(self.params, kf) for kf in mine]

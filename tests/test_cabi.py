@@ -25,7 +25,7 @@ def test_header_symbols_exported(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/*.h but not exported"
     lib.gsr_abi_version.restype = ctypes.c_int
-    assert lib.gsr_abi_version() == 5
+    assert lib.gsr_abi_version() == 6
 
 
 def test_headers_are_plain_c(tmp_path):
@@ -35,7 +35,7 @@ def test_headers_are_plain_c(tmp_path):
     src = tmp_path / "hdr_check.c"
     src.write_text('#include "gsrast_b200.h"\n#include "gsloss_b200.h"\n'
                    "int main(void) { gsr_loss_config c; gsr_gaussians g; gsr_camera k; gsr_grads d;\n"
-                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 5 ? 0 : 1; }\n")
+                   "  (void)c; (void)g; (void)k; (void)d; return GSR_ABI_VERSION == 6 ? 0 : 1; }\n")
     inc = os.path.join(ROOT, "include")
     if shutil.which("gcc"):
         subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
@@ -58,7 +58,7 @@ def test_c_client_links_and_runs(built_lib, tmp_path):
                     os.path.join(ROOT, "tests", "c_client.c"), "-o", exe, "-L", libdir, "-lgsrast_b200",
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    assert out.startswith("abi 5 ")
+    assert out.startswith("abi 6 ")
 
 
 def test_workspace_layouts_are_sane(built_lib):
@@ -105,7 +105,8 @@ def test_struct_mirrors_match_c_layout(built_lib):
     assert dgr._Gaussians.means3D.offset == 16 and dgr._Gaussians.scale_modifier.offset == 72
     assert ctypes.sizeof(dgr._Camera) == 16 + 4 * 8 + 8
     assert dgr._Camera.viewmatrix.offset == 16 and dgr._Camera.prefiltered.offset == 48
-    assert ctypes.sizeof(dgr._Grads) == 12 * 8 + 8 + 8 and dgr._Grads.accumulate.offset == 96 and dgr._Grads.dL_dextra.offset == 104
+    assert ctypes.sizeof(dgr._Grads) == 12 * 8 + 8 + 8 + 8 and dgr._Grads.accumulate.offset == 96 and dgr._Grads.dL_dextra.offset == 104
+    assert dgr._Grads.dL_dopacity_raw.offset == 112 and dgr._Gaussians.raw_params.offset == 12
     import gsr_slam_ops as ops
     assert ctypes.sizeof(ops._LossConfig) == 48 and ops._LossConfig.lambda_dssim.offset == 24   # 6 x int32, 5 x float, pad
 

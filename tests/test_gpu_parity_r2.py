@@ -236,3 +236,103 @@ def test_determinism_statement(dgr):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     worst = max(rel_err(a[2][k], b[2][k]) for k in a[2])
     assert worst < 1e-5, worst
+
+
+def _raw_case(dev, P=60000, W=320, H=240, deg=1, seed=5):
+    """Raw optimizer parameters the way the reference's model holds them (R/slam/gaussian_model.py:108-132): log scales,
+    un-normalised quaternions, logit opacities."""
+    from tests.util import scene_on
+    gs, cam, dL, bg = scene_on(dev, P, W, H, deg, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    raw = dict(gs)
+    raw["scales"] = torch.log(gs["scales"])
+    raw["rotations"] = gs["rotations"] * (0.5 + 1.5 * torch.rand(P, 1, generator=g).to(dev))
+    op = gs["opacities"].clamp(1e-4, 1 - 1e-4)
+    raw["opacities"] = torch.log(op / (1 - op))
+    return raw, cam, dL, bg
+
+
+def _torch_activated(rasterize, raw, rs, dL):
+    """The reference's composition: torch.sigmoid / torch.exp / F.normalize, then the rasterizer, autograd through all."""
+    import torch.nn.functional as F
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+    P = raw["means3D"].shape[0]
+    m2 = torch.zeros(P, 3, device=raw["means3D"].device, requires_grad=True)
+    color, radii = rasterize(leaves["means3D"], m2, torch.sigmoid(leaves["opacities"]), rs, shs=leaves["shs"],
+                             scales=torch.exp(leaves["scales"]), rotations=F.normalize(leaves["rotations"]))
+    color.backward(dL)
+    return color.detach(), radii.detach(), {k: v.grad for k, v in leaves.items()}
+
+
+def test_fused_activations_vs_torch_and_reference(dgr, ref):
+    """§8f-2: raw_params=True (sigmoid / exp / normalize applied inside the per-Gaussian kernels, gradients chained back
+    to the raw parameters) against (1) the same library fed torch-activated inputs with autograd through the torch
+    activations and (2) the compiled reference behind the same torch composition — which is exactly what
+    R/slam/renderer.py:157-175 + gaussian_model.py:108-132 execute."""
+    from tests.util import rel_err, rms_rel, settings_for
+    dev = torch.device("cuda:0")
+    raw, cam, dL, bg = _raw_case(dev)
+    rs = settings_for(dgr, cam, bg, 1, dev)
+    c_t, r_t, g_t = _torch_activated(_ours(dgr), raw, rs, dL)
+    c_r, r_r, g_r = _torch_activated(_theirs(ref), raw, rs, dL)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+    P = raw["means3D"].shape[0]
+    m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+    color, radii = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                                              raw_params=True)
+    color.backward(dL)
+    g = {k: v.grad for k, v in leaves.items()}
+    # exp / the norm may round differently from torch's kernels in the last bit: a handful of radii may move by one
+    assert (radii != r_t).float().mean() < 1e-4 and (radii != r_r).float().mean() < 1e-4
+    for c_ref in (c_t, c_r):
+        assert rms_rel(color, c_ref) < TOL and rel_err(color, c_ref) < 1e-3
+    for g_ref in (g_t, g_r):
+        for k in g_ref:
+            assert torch.isfinite(g[k]).all(), k
+            assert rms_rel(g[k], g_ref[k]) < 2e-4, (k, rms_rel(g[k], g_ref[k]))
+            assert rel_err(g[k], g_ref[k]) < 1e-3, (k, rel_err(g[k], g_ref[k]))
+    # accumulating variant (gradient bucket): two frames add up, the opacity chain included
+    tg = {k: torch.zeros_like(v) for k, v in raw.items()}
+    for _ in range(2):
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, _ = dgr.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                                              raw_params=True, grad_targets=tg)
+        color.backward(dL)
+    for k in g:
+        assert rms_rel(tg[k], 2 * g[k]) < 1e-5, (k, rms_rel(tg[k], 2 * g[k]))
+
+
+def test_streams_share_one_gradient_bucket(dgr):
+    """Frames back-propagated on different CUDA streams add into ONE gradient bucket: the per-Gaussian backward leaves
+    through TMA reduce-adds (float atomics for ragged chunks) and the blend backward through REDs, so concurrent adds do
+    not lose updates.  4 streams x 2 frames each against the same frames run one after the other on one stream."""
+    import gsr_synth as S
+    from gsr_mapstep import ShardedMapStep
+    from tests.util import rel_err
+    dev = torch.device("cuda:0")
+    P, W, H, K = 300001, 320, 240, 8            # P off the 256-Gaussian chunk: the ragged path is exercised too
+    gs = S.make_gaussians(P, W, H, seed=2, sh_degree=0)
+    cams = S.orbit_cameras(W, H, K, (0.0, 0.0, 4.0), radius=0.5)
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(9)).to(dev)
+    bg = torch.zeros(3, device=dev)
+    names = ["means3D", "shs", "opacities", "scales", "rotations"]
+    params = {k: gs[k].to(dev).requires_grad_(True) for k in names}
+    kfs = [dgr.GaussianRasterizationSettings(c.H, c.W, c.tanfovx, c.tanfovy, bg, 1.0, c.viewmatrix.to(dev),
+                                             c.projmatrix.to(dev), 0, c.campos.to(dev), False, False) for c in cams]
+
+    def forward_fn(p, rs, targets=None):
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, _ = dgr.GaussianRasterizer(rs)(means3D=p["means3D"], means2D=m2, opacities=p["opacities"], shs=p["shs"],
+                                              scales=p["scales"], rotations=p["rotations"], grad_targets=targets)
+        return color, dL
+
+    out = []
+    for streams in (1, 4):
+        st = ShardedMapStep(params, forward_fn=forward_fn, streams=streams, direct_targets=True)
+        for _ in range(3):
+            st.step(kfs)
+        torch.cuda.synchronize()
+        out.append(st.bucket.flat.clone())
+    assert rel_err(out[1], out[0]) < 1e-5, rel_err(out[1], out[0])
