@@ -484,6 +484,15 @@ def measure_iteration_ops(device, args, iters=20):
 
 
 # ------------------------------------------------------------------------------------------------
+_T0 = time.perf_counter()
+
+
+def phase(msg):
+    """Progress marks on stderr (wall clock since start): where a run's time goes outside the timed region."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -509,7 +518,9 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
+    phase("building the synthetic scene")
     gs_cpu, cams, dL_cpu = build_workload(args, device)
+    phase("scene built")
     bg = torch.zeros(3, device=device)
     dL = dL_cpu.to(device)
     names = ["means3D", "shs", "opacities", "scales", "rotations"]   # optimizer-group order of the reference
@@ -564,6 +575,7 @@ def main():
             return out
         launch_count = None
 
+    phase("instance counts")
     # instance counts for the byte accounting (one untimed forward per keyframe)
     R_list, vis_list = [], []
     if args.impl == "b200":
@@ -585,9 +597,11 @@ def main():
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     if rank == 0:
         sampler.start()
+    phase("warm-up")
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    phase("timed region")
     n0 = launch_count() if launch_count else 0
     # `repeats` timed blocks of EXACTLY --steps steps, each bracketed by barrier + synchronize on both sides and timed
     # with CUDA events on the launching stream; a block's time is the max over ranks, the line reports the median block.
@@ -611,6 +625,7 @@ def main():
             step()
         barrier()
     clocks = sampler.stop() if rank == 0 else None
+    phase("timed region done")
     frames = args.keyframes * args.steps
     value = frames / (ms / 1e3)
 
@@ -673,6 +688,7 @@ def main():
                                   "(includes waiting for the slowest rank); steps back to back as in the timed region, "
                                   "medians of 10 steps, max over ranks")
 
+    phase("stage profile")
     # ---- per-stage profile (untimed pass with the library's stage events on) --------------------
     lib = dgr._lib
     nst = lib.gsr_profile_num_stages()
@@ -729,6 +745,7 @@ def main():
     if distributed:
         dist.barrier()
 
+    phase("end-to-end leg")
     # ---- end to end through the public API with HOST buffers ------------------------------------
     if not args.no_e2e:
         host_in = {k: gs_cpu[k].contiguous().pin_memory() for k in names}
@@ -837,6 +854,7 @@ def main():
                                "parameters / of the reduced bucket over PCIe (bytes_per_step are per rank) and the "
                                "library's all-gather replicates the parameters over NVLink"}
 
+    phase("secondary metrics")
     extras = rank == 0 and world == 1 and not args.no_extras
     if extras:
         try:
@@ -864,6 +882,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args, gs_cpu, cams[0], dL_cpu)
         except Exception as ex:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(ex)}
+    phase("done")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if distributed:
