@@ -37,7 +37,7 @@ try:
     peer = hdl.get_buffer((rank + 1) % world, (16,), torch.float32)
     print(f"rank {rank} reads peer value {float(peer[0])}", flush=True)
     hdl.barrier()
-    for name in ("one_shot_all_reduce", "two_shot_all_reduce_", "multimem_all_reduce_"):
+    for name in (("one_shot_all_reduce", "two_shot_all_reduce_", "multimem_all_reduce_") if world < 8 else ()):
         try:
             op = getattr(torch.ops.symm_mem, name)
             for _ in range(3):
@@ -62,7 +62,9 @@ try:
     for p in (ROOT, os.path.join(ROOT, "mm3dgs-slam_b200")):
         sys.path.insert(0, p)
     from gsr_mapstep import PeerExchange
-    for mode in ("peer", "nvls"):
+    sweep = [("peer", 64), ("nvls", 64)] if world < 8 else [("nvls", b) for b in (32, 48, 64, 96)]
+    for mode, blocks in sweep:
+        os.environ["GSR_AR_BLOCKS"] = str(blocks)
         ex = PeerExchange(n, dev, None, mode)
         ex.flat.copy_(x)
         for _ in range(5):
@@ -75,8 +77,7 @@ try:
         e1.record()
         torch.cuda.synchronize()
         if rank == 0:
-            print(f"library exchange mode={mode} blocks={os.environ.get('GSR_AR_BLOCKS', 'default')}: "
-                  f"{e0.elapsed_time(e1) / 20 * 1e3:.1f} us", flush=True)
+            print(f"library exchange mode={mode} blocks={blocks}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us", flush=True)
         del ex
 except Exception as ex_:
     print(f"rank {rank}: library exchange failed: {repr(ex_)[:400]}", flush=True)
