@@ -16,6 +16,8 @@ static int ar_blocks()                      // CTAs actually launched: GSR_AR_BL
     if (v > kArMaxBlocks) v = kArMaxBlocks;
     return v;
 }
+constexpr int kArFlagWords = kArMaxBlocks * 2 * GSR_COMM_MAX_RANKS;
+
 struct ArArgs {
     float* bucket[GSR_COMM_MAX_RANKS];
     uint32_t* flags[GSR_COMM_MAX_RANKS];
