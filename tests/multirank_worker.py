@@ -60,15 +60,12 @@ if rank == 0:
     print("peer exchange ok:", modes)
 
 # keyframe-sharded map step: world ranks == single-rank accumulation over the same keyframes
-P, W, H, K = 20000, 160, 120, 4
+P, W, H = 20000, 160, 120
 gs = S.make_gaussians(P, W, H, seed=0, sh_degree=0)
-cams = S.orbit_cameras(W, H, K, (0.0, 0.0, 4.0), radius=0.5)
 dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
 bg = torch.zeros(3, device=dev)
 names = ["means3D", "shs", "opacities", "scales", "rotations"]
 params = {k: gs[k].to(dev).requires_grad_(True) for k in names}
-kfs = [dgr.GaussianRasterizationSettings(c.H, c.W, c.tanfovx, c.tanfovy, bg, 1.0, c.viewmatrix.to(dev), c.projmatrix.to(dev),
-                                         0, c.campos.to(dev), False, False) for c in cams]
 
 
 def forward_fn(p, rs, targets=None):
@@ -78,22 +75,29 @@ def forward_fn(p, rs, targets=None):
     return color, dL
 
 
-for exch in ("nccl", "auto"):
-    st = ShardedMapStep(params, forward_fn=forward_fn, streams=2, direct_targets=True, exchange=exch)
-    for _ in range(2):
-        st.step(kfs)
-    torch.cuda.synchronize()
-    got = st.bucket.flat.clone()
-    # single-rank ground truth: accumulate all K keyframes locally, no exchange
+# K keyframes: 2 per rank (several frames add into the bucket) and 1 per rank (overwrite mode, no zero fill)
+for K in (2 * world, world):
+    cams = S.orbit_cameras(W, H, K, (0.0, 0.0, 4.0), radius=0.5)
+    kfs = [dgr.GaussianRasterizationSettings(c.H, c.W, c.tanfovx, c.tanfovy, bg, 1.0, c.viewmatrix.to(dev),
+                                             c.projmatrix.to(dev), 0, c.campos.to(dev), False, False) for c in cams]
     solo = ShardedMapStep(params, forward_fn=forward_fn, streams=1, direct_targets=True, exchange="nccl")
-    solo.world, solo.rank = 1, 0
+    solo.world, solo.rank = 1, 0      # single-rank ground truth: accumulate all K keyframes locally, no exchange
     solo.step(kfs)
     torch.cuda.synchronize()
-    want = solo.bucket.flat
-    err = float((got - want).abs().max() / want.abs().max())
-    assert err < 1e-4, (exch, st.exchange, err)
-    if rank == 0:
-        print(f"map step exchange={st.exchange}: world {world} vs single-rank accumulation rel err {err:.2e}")
+    want = solo.bucket.flat.clone()
+    for exch in ("nccl", "auto"):
+        st = ShardedMapStep(params, forward_fn=forward_fn, streams=2, direct_targets=True, exchange=exch)
+        for _ in range(3):
+            st.step(kfs)
+        torch.cuda.synchronize()
+        got = st.bucket.flat.clone()
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < 1e-4, (K, exch, st.exchange, err)
+        ref = got.clone()
+        dist.broadcast(ref, 0)
+        assert exch == "nccl" or torch.equal(ref, got), "ranks hold different bits"
+        if rank == 0:
+            print(f"map step K={K} exchange={st.exchange}: world {world} vs single-rank accumulation rel err {err:.2e}")
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:

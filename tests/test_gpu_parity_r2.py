@@ -242,7 +242,7 @@ def _raw_case(dev, P=60000, W=320, H=240, deg=1, seed=5):
     """Raw optimizer parameters the way the reference's model holds them (R/slam/gaussian_model.py:108-132): log scales,
     un-normalised quaternions, logit opacities."""
     from tests.util import scene_on
-    gs, cam, dL, bg = scene_on(dev, P, W, H, deg, seed)
+    gs, cam, dL, bg = scene_on(dev, P, W, H, seed, deg)
     g = torch.Generator().manual_seed(seed + 1)
     raw = dict(gs)
     raw["scales"] = torch.log(gs["scales"])
