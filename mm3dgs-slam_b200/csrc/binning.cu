@@ -113,8 +113,13 @@ __device__ __forceinline__ void block_exclusive_scan(uint32_t* s_data, uint32_t*
 // inclusive prefix over blocks 0..block; anything else = not published yet for this pass (the array is zeroed once per
 // frame and reused by the four passes).
 constexpr uint32_t kStatMask = 0x0fffffffu;
-constexpr int kRadixBits = 8;
-constexpr int kRBins = 1 << kRadixBits;
+constexpr int kRadixBits = kSortBits;
+constexpr int kRBins = kSortBins;
+static_assert(kRBins == kSortThreads, "one thread per digit in the prefix / look-back sections");
+__device__ __forceinline__ uint32_t sort_digit(uint32_t key, int pass)
+{
+    return ((key - kSortKeyBase) >> (kRadixBits * pass)) & (uint32_t)(kRBins - 1);
+}
 
 __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
@@ -188,19 +193,23 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
                                                                uint32_t* counters, uint2* __restrict__ pairs_out,
                                                                TileCount tc)
 {
-    extern __shared__ int s_tdiff[];                      // pass 0 only: this block's tile-count difference array
-    __shared__ uint2 s_pairs[kSortChunk];                 // the block, reordered by digit (32 KB)
+    extern __shared__ __align__(16) unsigned char s_dynamic[];
+    uint2* s_pairs = reinterpret_cast<uint2*>(s_dynamic);                      // the block, reordered by digit (32 KB)
+    int* s_tdiff = reinterpret_cast<int*>(s_dynamic + sizeof(uint2) * kSortChunk);   // pass 0 only: tile-count difference array
     __shared__ uint16_t s_cnt[kSortWarps][kRBins];        // per-warp digit counters -> exclusive prefix over the warps
     __shared__ uint32_t s_lstart[kRBins];                 // first local slot of each digit
     __shared__ uint32_t s_gdst[kRBins];                   // global destination of local slot 0 of each digit's run
     __shared__ uint32_t s_warp[kRBins / 32];
+    __shared__ uint32_t s_next[PASS < kSortDigits - 1 ? kRBins : 1];   // this block's histogram of the NEXT digit
     __shared__ uint32_t s_block, s_total;
-    constexpr int shift = kRadixBits * PASS;
-    constexpr uint32_t mask = kRBins - 1;
     constexpr uint32_t tag_agg = (uint32_t)(2 * PASS + 1) << 28, tag_incl = (uint32_t)(2 * PASS + 2) << 28;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // the fourth pass has work only if some key does not fit 27 bits (a view depth beyond 6553): otherwise every key
+    // carries digit 0 and the list pass 2 wrote is the result (k_tile_partition makes the same test to pick the buffer)
+    if (PASS == kSortDigits - 1 && ghist[PASS * kRBins] == counters[kCntVisible]) return;
     if (tid == 0) s_block = atomicAdd(&counters[kCntTicket + PASS], 1u);
+    if (PASS < kSortDigits - 1) s_next[tid] = 0u;
     __syncthreads();
     const int block = (int)s_block;
     const int n = PASS == 0 ? n_in : (int)counters[kCntVisible];
@@ -224,7 +233,11 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
             val[j] = kv.y;
         }
     }
-    reinterpret_cast<uint4*>(&s_cnt[warp][0])[lane] = make_uint4(0u, 0u, 0u, 0u);   // this warp's 256 counters
+    {   // this warp's 512 counters
+        uint4* z = reinterpret_cast<uint4*>(&s_cnt[warp][0]);
+        z[lane] = make_uint4(0u, 0u, 0u, 0u);
+        z[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+    }
     ushort4 rect[PASS == 0 ? kSortItems : 1];
     if (PASS == 0) {
 #pragma unroll
@@ -274,14 +287,23 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
     for (int j = 0; j < kSortItems; j++) {
         const int i = wbase + j * 32 + lane;
         valid[j] = (i < n) && (PASS != 0 || key[j] != 0xffffffffu);
-        const uint32_t d = valid[j] ? ((key[j] >> shift) & mask) : 0xffffffffu;
+        const uint32_t d = valid[j] ? sort_digit(key[j], PASS) : 0xffffffffu;
         peers[j] = __match_any_sync(kFullMask, d);
+        if (PASS < kSortDigits - 1) {   // histogram of the next pass's digit (its keys are in registers here)
+            const uint32_t dn = valid[j] ? sort_digit(key[j], PASS + 1) : 0xffffffffu;
+            if (PASS == kSortDigits - 2) {          // the top digit takes one or two values: aggregate over the warp first
+                const unsigned pn = __match_any_sync(kFullMask, dn);
+                if (valid[j] && lane == __ffs(pn) - 1) atomicAdd(&s_next[dn], (uint32_t)__popc(pn));
+            } else if (valid[j]) {
+                atomicAdd(&s_next[dn], 1u);
+            }
+        }
     }
     __syncwarp();
     uint32_t ofs[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
-        const uint32_t d = (key[j] >> shift) & mask;
+        const uint32_t d = sort_digit(key[j], PASS);
         const int leader = __ffs(peers[j]) - 1;
         uint32_t old = 0;
         if (valid[j] && lane == leader) {
@@ -353,7 +375,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
 #pragma unroll
     for (int j = 0; j < kSortItems; j++) {
         if (valid[j]) {
-            const uint32_t d = (key[j] >> shift) & mask;
+            const uint32_t d = sort_digit(key[j], PASS);
             s_pairs[s_lstart[d] + s_cnt[warp][d] + ofs[j]] = make_uint2(key[j], val[j]);
         }
     }
@@ -361,7 +383,11 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint32_t* _
     const uint32_t total = s_total;
     for (uint32_t i = tid; i < total; i += kSortThreads) {
         const uint2 kv = s_pairs[i];
-        pairs_out[s_gdst[(kv.x >> shift) & mask] + i] = kv;
+        pairs_out[s_gdst[sort_digit(kv.x, PASS)] + i] = kv;
+    }
+    if (PASS < kSortDigits - 1) {   // (every thread passed block barriers after the last s_next update)
+        const uint32_t h = s_next[tid];
+        if (h) atomicAdd(const_cast<uint32_t*>(ghist) + (PASS + 1) * kRBins + tid, h);
     }
     if (PASS == 0) {
         // flush this block's difference array; the block that finishes last turns the sums into the tile ranges
@@ -385,30 +411,30 @@ template <int PASS>
 static void launch_sort_pass(const uint32_t* kin, const uint2* pin, int P, SortWS& w, uint32_t* counters, uint2* pout,
                              const TileCount& tc, cudaStream_t s)
 {
-    const size_t smem = PASS == 0 ? sizeof(int) * (size_t)(tc.gx + 1) * (tc.gy + 1) : 0;
+    const size_t smem = sizeof(uint2) * kSortChunk + (PASS == 0 ? sizeof(int) * (size_t)(tc.gx + 1) * (tc.gy + 1) : 0);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {   // 22 KB static + 32 KB (+ the difference array) dynamic: opt in
+        cudaFuncSetAttribute(k_sort_pass<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured[dev] = true;
+    }
     k_sort_pass<PASS><<<sort_chunks(P), kSortThreads, smem, s>>>(kin, pin, P, w.ghist, w.status, counters, pout, tc);
 }
 
-// Requires counters / ghist / status / tile_diff zeroed and ghist filled (k_preprocess_fwd).  Result: w.pairs_a holds
-// the counters[kCntVisible] visible Gaussians as {depth key, id} in (depth, index) order; ranges / w.tile_starts hold
-// every tile's place in the instance list.
+// Requires counters / ghist / status / tile_diff zeroed and digit 0 of ghist filled (k_preprocess_fwd).  Result:
+// w.pairs_a (w.pairs_b if the fourth pass had to run, see sorted_list()) holds the counters[kCntVisible] visible Gaussians
+// as {depth key, id} in (depth, index) order; ranges / w.tile_starts hold every tile's place in the instance list.
 int launch_depth_sort(const uint32_t* depth_keys, const ushort4* rects, int P, int gx, int gy, SortWS& w, uint2* ranges,
                       uint32_t* counters, cudaStream_t s)
 {
     if (P <= 0) return 0;
-    if (sizeof(int) * (size_t)(gx + 1) * (gy + 1) > 176 * 1024) return -1;   // tile grid too large for pass 0's shared memory
+    if (sizeof(int) * (size_t)(gx + 1) * (gy + 1) > 140 * 1024) return -1;   // tile grid too large for pass 0's shared memory
     TileCount tc{rects, gx, gy, w.tile_diff, ranges, w.tile_starts};
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(k_sort_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
-        configured[dev] = true;
-    }
-    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.pairs_b, tc, s);
-    launch_sort_pass<1>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, tc, s);
-    launch_sort_pass<2>(nullptr, w.pairs_a, P, w, counters, w.pairs_b, tc, s);
-    launch_sort_pass<3>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, tc, s);
+    launch_sort_pass<0>(depth_keys, nullptr, P, w, counters, w.pairs_a, tc, s);
+    launch_sort_pass<1>(nullptr, w.pairs_a, P, w, counters, w.pairs_b, tc, s);
+    launch_sort_pass<2>(nullptr, w.pairs_b, P, w, counters, w.pairs_a, tc, s);
+    launch_sort_pass<3>(nullptr, w.pairs_a, P, w, counters, w.pairs_b, tc, s);   // leaves at once unless a depth > 6553 exists
     return 0;
 }
 
@@ -550,7 +576,8 @@ __device__ __forceinline__ void warp_share_for_each(const uint32_t* s_id, const 
 constexpr uint32_t kTileAgg = 1u << 30, kTileIncl = 2u << 30, kTileVal = (1u << 30) - 1u;
 constexpr int kTileLook = 8;     // predecessors per look-back step
 
-__global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict__ perm, int per_cta,
+__global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict__ perm_a, const uint2* __restrict__ perm_b,
+                                                        const uint32_t* __restrict__ ghist, int per_cta,
                                                         const ushort4* __restrict__ rects, int gx, int T,
                                                         uint32_t* status, const uint32_t* __restrict__ tile_starts,
                                                         uint32_t* __restrict__ point_list, uint32_t* __restrict__ counters,
@@ -558,6 +585,8 @@ __global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict
 {
     if (counters[kCntR] > cap) return;   // instance list does not fit the caller's workspace: nothing is built
     const int n = (int)counters[kCntVisible];          // the depth sort kept only the visible Gaussians
+    // the sorted list is where the last sort pass that ran left it (the fourth one runs only for depths beyond 6553)
+    const uint2* __restrict__ perm = (ghist[(kSortDigits - 1) * kSortBins] == (uint32_t)n) ? perm_a : perm_b;
     extern __shared__ uint32_t s_dyn[];
     __shared__ uint32_t s_wsum[32];
     __shared__ int s_block;
@@ -718,7 +747,7 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
 
 // `cap`: number of instances the caller's point_list can hold.  If the scene has more (counters[kCntR], known on the
 // device only), the kernel returns without touching it.
-int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w,
+int launch_tile_partition(int P, const ushort4* rects, int gx, int gy, SortWS& w,
                           uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s)
 {
     const int T = gx * gy;
@@ -733,8 +762,8 @@ int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx
         cudaFuncSetAttribute(k_tile_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         configured[dev] = true;
     }
-    k_tile_partition<<<ctas, warps * 32, smem, s>>>(perm, per_cta, rects, gx, T, w.tile_status, w.tile_starts, point_list,
-                                                    counters, cap);
+    k_tile_partition<<<ctas, warps * 32, smem, s>>>(w.pairs_a, w.pairs_b, w.ghist, per_cta, rects, gx, T, w.tile_status,
+                                                    w.tile_starts, point_list, counters, cap);
     return 0;
 }
 

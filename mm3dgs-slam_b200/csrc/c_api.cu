@@ -339,8 +339,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
 
     prof_mark(ST_BEGIN, stream);
-    if (launch_tile_partition(gw.sort.pairs_a, P, gw.rects, gx, gy, gw.sort, gw.counters, (uint32_t)R, bw.point_list,
-                              stream) != 0)
+    if (launch_tile_partition(P, gw.rects, gx, gy, gw.sort, gw.counters, (uint32_t)R, bw.point_list, stream) != 0)
         return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 1);

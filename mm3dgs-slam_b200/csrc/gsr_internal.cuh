@@ -28,13 +28,18 @@ constexpr int kCntChunkFwd = 8;  // chunk ticket of k_preprocess_fwd
 constexpr int kCntChunkBwd = 9;  // chunk ticket of k_preprocess_bwd (wraps to zero by itself)
 constexpr int kCntTotalsDone = 10; // blocks of depth-sort pass 0 that have finished (the last one builds the tile ranges)
 constexpr int kCntPartTicket = 11; // block ticket of the tile partition
-constexpr int kSortDigits = 4;   // 8-bit digits of the depth sort
-constexpr int kSortBins = 256;
+// Depth sort: the keys are the float bits of view depths > 0.1, so `bits - kSortKeyBase` is a small non-negative number
+// (< 2^27 for every depth below 6553) whose order — ties included — is the order of the keys: three 9-bit digits sort
+// it, and a fourth pass over the top 5 bits runs only when a deeper Gaussian exists.
+constexpr int kSortDigits = 4;
+constexpr int kSortBits = 9;
+constexpr int kSortBins = 1 << kSortBits;
+constexpr uint32_t kSortKeyBase = 0x3DCCCCCDu;   // float bits of 0.1f: every visible depth is larger (CR/auxiliary.h:154)
 constexpr int kTileDiffReplicas = 8;   // copies of the tile-count difference array (spreads the flush REDs)
 
 struct SortWS {
     uint2 *pairs_a, *pairs_b;                      // depth-sort ping-pong of {depth key, Gaussian id} (P each); result in pairs_a
-    uint32_t* ghist;                               // [4][256] global digit histograms of the visible depth keys
+    uint32_t* ghist;                               // [4][512] global digit histograms of the visible depth keys
     uint32_t* status;                              // [sort_chunks(P)][256] look-back state of the sort passes
     size_t status_words;
     int* tile_diff;                                // [kTileDiffReplicas][(gy+1)*(gx+1)] difference arrays of the per-tile instance counts
@@ -82,7 +87,7 @@ struct PreArgs {
     ushort4* rects;
     uint32_t* depth_keys;
     uint32_t* num_rendered;   // device counter, zeroed by the caller
-    uint32_t* ghist;          // [4][256] digit histograms of the visible depth keys (8 bits each), zeroed by the caller
+    uint32_t* ghist;          // [4][512] digit histograms of the depth sort; this kernel fills digit 0, zeroed by the caller
     uint32_t* status;         // look-back state of the depth sort: zeroed by this kernel (status_words u32)
     size_t status_words;
     uint32_t* chunk_ticket;   // chunk scheduler of the persistent kernel, zeroed by the caller
@@ -94,7 +99,7 @@ void launch_mark_visible(int P, const float* means, const float* view, const flo
 
 int launch_depth_sort(const uint32_t* depth_keys, const ushort4* rects, int P, int gx, int gy, SortWS& w, uint2* ranges,
                       uint32_t* counters, cudaStream_t s);
-int launch_tile_partition(const uint2* perm, int P, const ushort4* rects, int gx, int gy, SortWS& w,
+int launch_tile_partition(int P, const ushort4* rects, int gx, int gy, SortWS& w,
                           uint32_t* counters, uint32_t cap, uint32_t* point_list, cudaStream_t s);
 
 void launch_render_fwd(int W, int H, int gx, int gy, const uint2* ranges, const uint32_t* point_list,

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
     __shared__ float s_cam[35];
     __shared__ uint32_t s_tiles;
     __shared__ int s_chunk[2];                            // chunk index of each stage (tickets: dynamic scheduling)
-    __shared__ uint32_t s_hist[kSortDigits * kSortBins];  // this CTA's share of the depth sort's digit histograms
+    __shared__ uint32_t s_hist[kSortBins];                // this CTA's share of the depth sort's first digit histogram
 
     const int tid = threadIdx.x;
     const bool has_sr = (a.cov3D_pre == nullptr);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
-    for (int i = tid; i < kSortDigits * kSortBins; i += kPB) s_hist[i] = 0u;
+    for (int i = tid; i < kSortBins; i += kPB) s_hist[i] = 0u;
 
     const uint32_t stage_bytes = (uint32_t)sizeof(float) * kPB * (3 + 1) + (has_sr ? (uint32_t)sizeof(float) * kPB * 7 : 0u) +
                                  (col_staged ? (uint32_t)sizeof(float) * kPB * 3 : 0u);
@@ -199,20 +199,9 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
                 a.extra_gen[(size_t)idx * 3 + 2] = z * z;
             }
         }
-        {   // digit histograms of the depth sort (four 8-bit digits), while the key is in a register: shared-memory
-            // atomics, flushed once per CTA.  The two low digits are mantissa bits (spread over the 256 counters); the
-            // two high ones (exponent, top mantissa bits) take few values inside a warp, so they are aggregated first.
-            const bool v = dkey != 0xffffffffu;
-            if (v) {
-                atomicAdd(&s_hist[dkey & 255u], 1u);
-                atomicAdd(&s_hist[256u + ((dkey >> 8) & 255u)], 1u);
-            }
-            const int lane_ = tid & 31;
-            const uint32_t d2 = v ? ((dkey >> 16) & 255u) : 0xffffffffu, d3 = v ? (dkey >> 24) : 0xffffffffu;
-            const unsigned p2 = __match_any_sync(0xffffffffu, d2), p3 = __match_any_sync(0xffffffffu, d3);
-            if (v && lane_ == __ffs(p2) - 1) atomicAdd(&s_hist[512u + d2], (uint32_t)__popc(p2));
-            if (v && lane_ == __ffs(p3) - 1) atomicAdd(&s_hist[768u + d3], (uint32_t)__popc(p3));
-        }
+        // histogram of the depth sort's first digit (the low 9 bits of the normalised key: mantissa bits, spread over the
+        // 512 counters), while the key is in a register; every sort pass builds the histogram of the NEXT digit itself
+        if (dkey != 0xffffffffu) atomicAdd(&s_hist[(dkey - kSortKeyBase) & (uint32_t)(kSortBins - 1)], 1u);
         // the bulk store issued two iterations ago has finished reading this output stage
         if (tid == 0) bulk_wait_read<1>();
         __syncthreads();   // (also: every thread is done with the input stage)
@@ -238,7 +227,7 @@ __global__ void __launch_bounds__(kPB, 4) k_preprocess_fwd(PreArgs a, int nchunk
         if ((tid & 31) == 0 && wsum) atomicAdd(&s_tiles, wsum);
         __syncthreads();
         if (tid == 0 && s_tiles) atomicAdd(a.num_rendered, s_tiles);
-        for (int i = tid; i < kSortDigits * kSortBins; i += kPB) {
+        for (int i = tid; i < kSortBins; i += kPB) {
             const uint32_t h = s_hist[i];
             if (h) atomicAdd(&a.ghist[i], h);
         }

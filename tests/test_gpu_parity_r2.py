@@ -336,3 +336,38 @@ def test_streams_share_one_gradient_bucket(dgr):
         torch.cuda.synchronize()
         out.append(st.bucket.flat.clone())
     assert rel_err(out[1], out[0]) < 1e-5, rel_err(out[1], out[0])
+
+
+@pytest.mark.parametrize("far", [False, True])
+def test_depth_sort_three_and_four_passes(dgr, ref, far):
+    """The depth sort orders `float bits - bits(0.1f)` with three 9-bit digits and runs a fourth pass only when a key
+    needs more than 27 bits (a view depth beyond 6553).  Both cases against the compiled reference: the per-tile lists
+    must be bit-identical, ties (exactly equal depths) included.  far=True scales the scene by 2000 so that depths reach
+    ~16000 and the fourth pass has work."""
+    from tests import ws_decode
+    from tests.util import scene_on, settings_for
+    dev = torch.device("cuda:0")
+    P, W, H = 40000, 320, 240
+    gs, cam, dL, bg = scene_on(dev, P, W, H, 17, 0)
+    gs["means3D"][1::7, 2] = gs["means3D"][0::7, 2][: gs["means3D"][1::7].shape[0]]      # exact depth ties
+    if far:
+        gs["means3D"] = gs["means3D"] * 2000.0
+        gs["scales"] = gs["scales"] * 2000.0
+    rs = settings_for(dgr, cam, bg, 0, dev)
+    with torch.no_grad():
+        R, color, radii, geom, binning, img = dgr._forward_native(
+            gs["means3D"], gs["shs"], None, gs["opacities"], gs["scales"], gs["rotations"], None, rs,
+            rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+        f = ref.forward(gs["means3D"], gs["opacities"], rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg, W, H,
+                        cam.tanfovx, cam.tanfovy, gs["scales"], gs["rotations"], 1.0, None, gs["shs"], 0)
+    torch.cuda.synchronize()
+    assert R == f["num_rendered"] and R > 0
+    mg = ws_decode.decode_geom(geom, P, W, H)
+    vis = (radii > 0).cpu()
+    depth = mg["depths"][vis]
+    assert bool((depth.max() > 6553.6) == far)
+    mi, ri = ws_decode.decode_img(img, W, H), ref.decode_img(f["img"], W, H)
+    assert torch.equal(mi["ranges"], ri["ranges"][: mi["ranges"].shape[0]])
+    mb, rb = ws_decode.decode_binning(binning, R, mg, mi), ref.decode_binning(f["binning"], R)
+    assert torch.equal(mb["point_list"], rb["point_list"])
+    assert torch.equal(mi["n_contrib"], ri["n_contrib"])
