@@ -102,18 +102,20 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     w.rec = carve<float4>(p, n * 3);
     w.rects = carve<ushort4>(p, n);
     w.depth_keys = carve<uint32_t>(p, n);
-    // counters | ghist | tile_diff | tile_status are contiguous: one memset zeroes them at the start of a forward (the
-    // projection kernel adds to the first three); the sort's look-back state is zeroed by the projection kernel itself
+    // counters | ghist | tile_diff are contiguous: one small memset zeroes them at the start of a forward
     int ctas, per_cta, warps;
     size_t smem;
     tile_partition_plan((int)n, T, ctas, per_cta, warps, smem);
     w.counters = carve<uint32_t>(p, 64);          // [63] = CTA counter of the camera-gradient reduction
     w.sort.ghist = carve<uint32_t>(p, kSortDigits * kSortBins);
     w.sort.tile_diff = carve<int>(p, (size_t)kTileDiffReplicas * ((W + kTile - 1) / kTile + 1) * ((H + kTile - 1) / kTile + 1));
-    w.sort.tile_status = carve<uint32_t>(p, (size_t)ctas * T);
     w.zero_bytes = (size_t)(p - reinterpret_cast<char*>(w.counters));
-    w.sort.status_words = (size_t)sort_chunks((int)n) * kSortBins;
-    w.sort.status = carve<uint32_t>(p, w.sort.status_words);
+    // look-back state of the depth sort and of the tile partition, contiguous: zeroed by the projection kernel itself
+    // (a few MB of stores spread over its CTAs instead of a separate memset in front of it)
+    w.sort.status = reinterpret_cast<uint32_t*>(p);
+    carve<uint32_t>(p, (size_t)sort_chunks((int)n) * kSortBins);
+    w.sort.tile_status = carve<uint32_t>(p, (size_t)ctas * T);
+    w.sort.status_words = (size_t)(p - reinterpret_cast<char*>(w.sort.status)) / sizeof(uint32_t);
     w.extra_gen = carve<float>(p, n * 3);
     w.sort.pairs_a = carve<uint2>(p, n);
     w.sort.pairs_b = carve<uint2>(p, n);
@@ -281,7 +283,7 @@ int gsr_forward_preprocess(gsr_stream_t stream_, const gsr_gaussians* g, const g
     a.chunk_ticket = gw.counters + kCntChunkFwd;
     a.extra_gen = g->extra_mode == 1 ? gw.extra_gen : nullptr;
     prof_mark(ST_BEGIN, stream);
-    // counters, digit histograms, tile-count difference array, look-back state of the tile partition (a few MB)
+    // counters, digit histograms, tile-count difference array (~50 KB)
     GSR_CUDA(cudaMemsetAsync(gw.counters, 0, gw.zero_bytes, stream));
     launch_preprocess_fwd(a, stream);
     GSR_STAGE("preprocess", cam->debug, stream);
