@@ -27,6 +27,8 @@
 // instead of the reference's ~150 B per instance (6 onesweep passes over 12-byte pairs).
 #include "gsr_internal.cuh"
 #include "gsr_math.cuh"
+#include <algorithm>
+#include <stdlib.h>
 
 namespace gsr {
 
@@ -577,7 +579,7 @@ constexpr uint32_t kTileAgg = 1u << 30, kTileIncl = 2u << 30, kTileVal = (1u << 
 constexpr int kTileLook = 8;     // predecessors per look-back step
 
 __global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict__ perm_a, const uint2* __restrict__ perm_b,
-                                                        const uint32_t* __restrict__ ghist, int per_cta,
+                                                        const uint32_t* __restrict__ ghist, int cap_cta,
                                                         const ushort4* __restrict__ rects, int gx, int T,
                                                         uint32_t* status, const uint32_t* __restrict__ tile_starts,
                                                         uint32_t* __restrict__ point_list, uint32_t* __restrict__ counters,
@@ -594,12 +596,15 @@ __global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict
     if (tid == 0) s_block = (int)atomicAdd(&counters[kCntPartTicket], 1u);
     __syncthreads();
     const int block = s_block;
+    // chunk size: the visible Gaussians divided evenly over the grid (the host sized the grid as whole waves of CTAs
+    // without knowing how many Gaussians are visible), at most what the shared-memory layout was sized for
+    const int per_cta = min(cap_cta, ((n + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31);
     const int c0 = block * per_cta;
     if (c0 >= n) return;                   // (so is every later ticket: nobody will look back at this row)
     uint32_t* s_id = s_dyn;
-    uint32_t* s_pk = s_id + per_cta;
-    uint32_t* s_ex = s_pk + per_cta;       // [per_cta + 1] exclusive instance offsets inside the chunk
-    uint32_t* s_base = s_ex + ((per_cta + 1 + 3) & ~3);
+    uint32_t* s_pk = s_id + cap_cta;
+    uint32_t* s_ex = s_pk + cap_cta;       // [per_cta + 1] exclusive instance offsets inside the chunk
+    uint32_t* s_base = s_ex + ((cap_cta + 1 + 3) & ~3);
     const int Tp = (T + 7) & ~7;           // row pitch: keeps every row 16-byte aligned
     uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_base + Tp);
     uint8_t* s_tag = reinterpret_cast<uint8_t*>(s_cnt + (size_t)nwarps * Tp);
@@ -728,20 +733,26 @@ void tile_partition_plan(int P, int T, int& ctas, int& per_cta, int& warps, size
 {
     // as many warps per CTA as their private per-tile counters (3 bytes per tile) allow in ~200 KB of shared memory
     // next to the chunk's rectangles, at most 32: the kernel is a latency-bound walk, so short per-warp shares matter
-    // more than anything else.
-    const int max_ctas = 4 * 148;   // (sizing to exactly one resident wave measured slower)
+    // more than anything else.  `per_cta` is the CAPACITY of a chunk (what shared memory is laid out for); the kernel
+    // divides the visible Gaussians evenly over the grid, and the grid is a whole number of waves of CTAs (one CTA per SM)
+    // so that no partial last wave leaves most SMs idle: 346 chunks of 2048 on 148 SMs were 2.3 waves.
+    static int waves = 0;
+    if (waves == 0) {
+        const char* e = getenv("GSR_PART_WAVES");
+        waves = e ? atoi(e) : 2;
+        if (waves < 1) waves = 1;
+    }
     warps = 32;
     for (;;) {
-        per_cta = 64 * warps;
-        if (per_cta < 1024) per_cta = 1024;
-        if ((P + per_cta - 1) / per_cta > max_ctas) per_cta = (P + max_ctas - 1) / max_ctas;
-        per_cta = (per_cta + 31) / 32 * 32;
-        while (tile_partition_smem(T, per_cta, warps) > 200 * 1024 && per_cta > 1024) per_cta = (per_cta / 2 + 31) / 32 * 32;
+        per_cta = 4096;
+        while (tile_partition_smem(T, per_cta, warps) > 200 * 1024 && per_cta > 1024) per_cta -= 256;
         if (tile_partition_smem(T, per_cta, warps) <= 200 * 1024 || warps == 1) break;
         warps >>= 1;
     }
     if (tile_partition_smem(T, per_cta, warps) > 200 * 1024 || T > 65535) warps = 0;   // does not fit at all
-    ctas = P > 0 ? (P + per_cta - 1) / per_cta : 0;
+    const int need = P > 0 ? (P + per_cta - 1) / per_cta : 0;                 // every Gaussian may be visible
+    const int want = P > 0 ? std::min(waves * device_sm_count(), (P + 1023) / 1024) : 0;
+    ctas = std::max(need, want);
     smem = tile_partition_smem(T, per_cta, warps > 0 ? warps : 1);
 }
 
