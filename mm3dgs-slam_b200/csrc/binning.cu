@@ -125,6 +125,16 @@ __device__ __forceinline__ uint32_t sort_digit(uint32_t key, int pass)
 
 __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ uint4 ld_status4(const uint32_t* p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status4(uint32_t* p, const uint4& v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // Pass 0 additionally derives the per-tile instance counts from the tile rectangles (TileCount below): a splat adds one
 // instance to every tile of its rectangle [x0, x1) x [y0, y1), which as a 2-D difference array is four corner updates
@@ -669,8 +679,7 @@ __global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict
             warp_rank_tile(my, my_tag, tile, valid, tbits);
         });
     __syncthreads();
-    // per tile: exclusive prefix over the warps; the sum is this CTA's count -> publish, look back, final base
-    uint32_t* my_status = status + (size_t)block * T;
+    // per tile: exclusive prefix over the warps; the sum is this CTA's count
     for (int t = tid; t < T; t += blockDim.x) {
         uint32_t acc = 0;
 #pragma unroll 8
@@ -679,40 +688,60 @@ __global__ void __launch_bounds__(1024) k_tile_partition(const uint2* __restrict
             s_cnt[(size_t)w * Tp + t] = (uint16_t)acc;
             acc += c;
         }
-        st_status(my_status + t, (block == 0 ? kTileIncl : kTileAgg) | acc);
         s_base[t] = acc;
     }
-    for (int t = tid; t < T; t += blockDim.x) {
-        const uint32_t agg = s_base[t];
-        uint32_t excl = 0;
+    __syncthreads();
+    // publish, look back, final base — FOUR tiles per thread with 16-byte accesses: with thousands of tiles and few
+    // warps (1920x1080: 8160 tiles, 4 warps) the look-back is the CTA's longest phase, and its cost is the number of
+    // dependent L2 round trips per thread.  Every 32-bit word carries its own tag, so a torn 16-byte store is harmless.
+    const int pitch = (T + 3) & ~3;
+    uint32_t* my_status = status + (size_t)block * pitch;
+    for (int q4 = tid; q4 * 4 < T; q4 += blockDim.x) {
+        const int t0 = q4 * 4;
+        uint32_t agg[4], excl[4] = {0u, 0u, 0u, 0u};
+        bool fin[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            agg[c] = (t0 + c < T) ? s_base[t0 + c] : 0u;
+            fin[c] = false;
+        }
+        const uint32_t tag0 = block == 0 ? kTileIncl : kTileAgg;
+        st_status4(my_status + t0, make_uint4(tag0 | agg[0], tag0 | agg[1], tag0 | agg[2], tag0 | agg[3]));
         int p = block - 1;
-        while (p >= 0) {   // kTileLook predecessors per step; block 0 always publishes an inclusive value
-            uint32_t v[kTileLook];
+        while (p >= 0 && !(fin[0] && fin[1] && fin[2] && fin[3])) {   // kTileLook predecessors per step
+            uint4 v[kTileLook];
 #pragma unroll
             for (int u = 0; u < kTileLook; u++)
-                v[u] = (p - u >= 0) ? ld_status(status + (size_t)(p - u) * T + t) : kTileIncl;
+                v[u] = (p - u >= 0) ? ld_status4(status + (size_t)(p - u) * pitch + t0)
+                                    : make_uint4(kTileIncl, kTileIncl, kTileIncl, kTileIncl);   // before block 0: nothing
             int used = 0;
-            bool done = false, stalled = false;
+            bool stalled = false;
 #pragma unroll
             for (int u = 0; u < kTileLook; u++) {
-                if (done || stalled) continue;
-                const uint32_t tag = v[u] & ~kTileVal;
-                if (tag == kTileIncl) {
-                    excl += v[u] & kTileVal;
-                    done = true;
-                } else if (tag == kTileAgg) {
-                    excl += v[u] & kTileVal;
-                    used++;
-                } else {
-                    stalled = true;
+                if (stalled) continue;
+                const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                if (!(w4[0] & ~kTileVal) || !(w4[1] & ~kTileVal) || !(w4[2] & ~kTileVal) || !(w4[3] & ~kTileVal)) {
+                    stalled = true;          // not (completely) published yet
+                    continue;
                 }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (!fin[c]) {
+                        excl[c] += w4[c] & kTileVal;
+                        if ((w4[c] & ~kTileVal) == kTileIncl) fin[c] = true;
+                    }
+                }
+                used++;
             }
-            if (done) break;
             p -= used;
             if (stalled) __nanosleep(40);
         }
-        if (block > 0) st_status(my_status + t, kTileIncl | (excl + agg));
-        s_base[t] = tile_starts[t] + excl;
+        if (block > 0)
+            st_status4(my_status + t0, make_uint4(kTileIncl | (excl[0] + agg[0]), kTileIncl | (excl[1] + agg[1]),
+                                                  kTileIncl | (excl[2] + agg[2]), kTileIncl | (excl[3] + agg[3])));
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (t0 + c < T) s_base[t0 + c] = tile_starts[t0 + c] + excl[c];
     }
     __syncthreads();
     if (len != 0)

@@ -114,7 +114,7 @@ GeomWS geom_ws_carve(char* base, int P, int W, int H)
     // (a few MB of stores spread over its CTAs instead of a separate memset in front of it)
     w.sort.status = reinterpret_cast<uint32_t*>(p);
     carve<uint32_t>(p, (size_t)sort_chunks((int)n) * kSortBins);
-    w.sort.tile_status = carve<uint32_t>(p, (size_t)ctas * T);
+    w.sort.tile_status = carve<uint32_t>(p, (size_t)ctas * ((T + 3) & ~3));   // rows padded to 16 bytes
     w.sort.status_words = (size_t)(p - reinterpret_cast<char*>(w.sort.status)) / sizeof(uint32_t);
     w.extra_gen = carve<float>(p, n * 3);
     w.sort.pairs_a = carve<uint2>(p, n);
