@@ -201,6 +201,11 @@ typedef struct gsr_geom_layout {
 } gsr_geom_layout;
 typedef struct gsr_img_layout { size_t final_T, n_contrib, ranges, total; } gsr_img_layout;
 typedef struct gsr_binning_layout { size_t point_list, total; } gsr_binning_layout;
+/* How the one-kernel tile partition is laid out for a problem size (host-side planning only; tests check that it fits
+ * the hardware for every size the library accepts): CTAs launched, Gaussians a CTA's shared memory is sized for,
+ * warps per CTA (0 = the tile grid does not fit: gsr_forward_render fails), dynamic shared memory per CTA. */
+typedef struct gsr_partition_plan { int32_t ctas, chunk_capacity, warps, _pad; size_t smem_bytes; } gsr_partition_plan;
+void gsr_partition_plan_of(int32_t P, int32_t width, int32_t height, gsr_partition_plan* out);
 void gsr_geom_layout_of(int32_t P, int32_t width, int32_t height, gsr_geom_layout* out);
 void gsr_img_layout_of(int32_t width, int32_t height, gsr_img_layout* out);
 void gsr_binning_layout_of(int64_t R, gsr_binning_layout* out);

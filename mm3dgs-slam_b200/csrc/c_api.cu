@@ -227,6 +227,15 @@ size_t gsr_geom_ws_bytes(int32_t P, int32_t W, int32_t H) { return geom_ws_carve
 size_t gsr_img_ws_bytes(int32_t W, int32_t H) { return img_ws_carve(nullptr, W, H).total; }
 size_t gsr_binning_ws_bytes(int64_t R) { return bin_ws_carve(nullptr, R).total; }
 
+void gsr_partition_plan_of(int32_t P, int32_t W, int32_t H, gsr_partition_plan* o)
+{
+    int ctas = 0, per_cta = 0, warps = 0;
+    size_t smem = 0;
+    const int T = ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+    tile_partition_plan(P > 0 ? P : 1, T, ctas, per_cta, warps, smem);
+    o->ctas = ctas; o->chunk_capacity = per_cta; o->warps = warps; o->_pad = 0; o->smem_bytes = smem;
+}
+
 void gsr_geom_layout_of(int32_t P, int32_t W, int32_t H, gsr_geom_layout* o)
 {
     GeomWS w = geom_ws_carve(nullptr, P, W, H);
@@ -342,7 +351,7 @@ int gsr_forward_render(gsr_stream_t stream_, const gsr_gaussians* g, const gsr_c
 
     prof_mark(ST_BEGIN, stream);
     if (launch_tile_partition(P, gw.rects, gx, gy, gw.sort, gw.counters, (uint32_t)R, bw.point_list, stream) != 0)
-        return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (> ~33k tiles)");
+        return fail(GSR_ERR_INVALID, "tile grid too large for the shared-memory tile partition (more than ~26k tiles of 16x16 pixels)");
     GSR_STAGE("tile_partition", cam->debug, stream);
     GSR_MARK(ST_TILE_PARTITION, stream, 1);
     launch_render_fwd(W, H, gx, gy, iw.ranges, bw.point_list, gw.rec, cam->background, iw.final_T, iw.n_contrib,

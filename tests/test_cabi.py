@@ -215,3 +215,33 @@ def test_flat_adam_surgery_has_no_cpu_path(built_lib):
         opt.prune(torch.ones(10, dtype=torch.bool))
     with pytest.raises(RuntimeError):
         opt.extend({k: v[:2] for k, v in params.items()})
+
+
+def test_tile_partition_plan_fits_the_hardware(built_lib):
+    """gsr_partition_plan_of: for every problem size the library accepts the one-kernel tile partition must fit a B200
+    SM (<= 220 KB dynamic shared memory, <= 1024 threads), its chunks must cover the case that every Gaussian is visible,
+    a chunk must stay within the 16-bit CTA-relative ranks, and its look-back rows must fit the geometry workspace."""
+    lib = ctypes.CDLL(built_lib)
+
+    class Plan(ctypes.Structure):
+        _fields_ = [("ctas", ctypes.c_int32), ("chunk_capacity", ctypes.c_int32), ("warps", ctypes.c_int32),
+                    ("_pad", ctypes.c_int32), ("smem_bytes", ctypes.c_size_t)]
+    lib.gsr_geom_ws_bytes.restype = ctypes.c_size_t
+    lib.gsr_geom_ws_bytes.argtypes = [ctypes.c_int32] * 3
+    for W, H in ((16, 16), (128, 96), (320, 240), (640, 330), (640, 480), (1920, 1080), (2560, 1440), (3840, 1600), (100, 70)):
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        for P in (1, 300, 2048, 4097, 100_000, 1_000_000, 5_000_000, 50_000_000):
+            p = Plan()
+            lib.gsr_partition_plan_of(ctypes.c_int32(P), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(p))
+            assert 1 <= p.warps <= 32, (P, W, H, p.warps)
+            assert p.smem_bytes <= 220 * 1024
+            assert 1024 <= p.chunk_capacity <= 65535 and p.chunk_capacity % 32 == 0
+            assert p.ctas >= 1 and p.ctas * p.chunk_capacity >= P                  # every Gaussian may be visible
+            assert p.smem_bytes >= 12 * p.chunk_capacity + 4 * T + 3 * T * p.warps  # rectangles + bases + counters + tags
+            assert lib.gsr_geom_ws_bytes(P, W, H) >= 4 * p.ctas * T                # look-back rows live in the geometry ws
+    # a tile grid too large for one warp's counters (more than ~26k tiles, e.g. 3840x2160 = 32400) is reported as such
+    # (warps == 0 -> gsr_forward_render returns GSR_ERR_INVALID), not mis-planned
+    for W, H in ((3840, 2160), (16000, 16000)):
+        p = Plan()
+        lib.gsr_partition_plan_of(ctypes.c_int32(1000), ctypes.c_int32(W), ctypes.c_int32(H), ctypes.byref(p))
+        assert p.warps == 0

@@ -127,3 +127,59 @@ def test_densification_stats_reduction(tmp_path):
     for a, b in zip(got, want):
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
     assert float(want[1].max()) <= 4 and float(want[2].max()) <= 4
+
+
+def _targets_forward_fn(dL, W, H, scale):
+    """A CPU stand-in for the library's grad_targets contract (rasterize_gaussians docstring): the gradients of a frame
+    are ADDED into the accumulators the step hands out, or — when the dict carries _overwrite — stored, except for the
+    opacity accumulator, which is always added into (the blend backward reduces into it) and which the step zeroes."""
+    from oracle import gs_oracle as O
+
+    def fwd(p, cam, targets):
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+
+        def sink(k, store):
+            def hook(g):
+                with torch.no_grad():
+                    (targets[k].copy_ if store else targets[k].add_)(g.to(targets[k].dtype))
+            return hook
+        for k, leaf in leaves.items():
+            leaf.register_hook(sink(k, bool(targets.get("_overwrite")) and k != "opacities"))
+        img = O.differentiable_render(leaves["means3D"], leaves["opacities"], leaves["scales"], leaves["rotations"],
+                                      leaves["shs"], 0, cam.viewmatrix, cam.projmatrix, cam.campos, torch.zeros(3), W, H,
+                                      cam.tanfovx, cam.tanfovy)
+        return img, dL.double() * scale[0]
+    return fwd
+
+
+def _targets_worker(rank, world, port, out, K):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gs, cams, dL, W, H = _scene()
+    scale = [3.0]
+    step = ShardedMapStep(_params(gs), forward_fn=_targets_forward_fn(dL, W, H, scale), direct_targets=True)
+    step.step(cams[:K])            # a first step with other gradients: nothing of it may survive into the second
+    scale[0] = 1.0
+    step.step(cams[:K])
+    if rank == 0:
+        torch.save((step.bucket.flat.clone(), step._single), out)
+    dist.destroy_process_group()
+
+
+def test_direct_targets_single_keyframe_overwrites(tmp_path):
+    """direct_targets: a rank that owns ONE keyframe runs in overwrite mode (only the opacity slice of the bucket is
+    zeroed), a rank with several accumulates into a zeroed bucket; either way two consecutive steps at world_size 2
+    equal single-rank accumulation of the second step's gradients."""
+    gs, cams, dL, W, H = _scene()
+    for K, single in ((2, True), (4, False)):
+        ref = ShardedMapStep(_params(gs), _frame_fn(dL, W, H))
+        ref.step(cams[:K])
+        want = ref.bucket.flat.clone()
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        out = str(tmp_path / f"bucket_{K}.pt")
+        mp.spawn(_targets_worker, args=(2, port, out, K), nprocs=2, join=True)
+        got, was_single = torch.load(out)
+        assert was_single == single
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6 * float(want.abs().max())), K
