@@ -737,7 +737,10 @@ def main():
             line["blend"] = measure_blend(dgr, params, kfs[0], stages, device)
         except Exception as ex:
             line["blend"] = {"error": repr(ex)}
-        line["parity_check"] = parity_check(dgr, params, kfs[0], dL, device)
+        try:
+            line["parity_check"] = parity_check(dgr, params, kfs[0], dL, device)
+        except Exception as ex:   # the checker itself failed (e.g. the compiled reference could not be loaded): say so
+            line["parity_check"] = {"checked": False, "why": repr(ex)[:300]}
         if line["parity_check"].get("checked") and not line["parity_check"]["ok"]:
             print(json.dumps({"error": "parity check against oracle/_ref failed", "parity_check": line["parity_check"]}),
                   flush=True)
