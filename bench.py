@@ -741,12 +741,16 @@ def main():
             line["parity_check"] = parity_check(dgr, params, kfs[0], dL, device)
         except Exception as ex:   # the checker itself failed (e.g. the compiled reference could not be loaded): say so
             line["parity_check"] = {"checked": False, "why": repr(ex)[:300]}
-        if line["parity_check"].get("checked") and not line["parity_check"]["ok"]:
+    parity_failed = bool(rank == 0 and line.get("parity_check", {}).get("checked") and not line["parity_check"]["ok"])
+    if distributed:   # every rank learns the verdict (this is also the barrier behind rank 0's extra work)
+        flag = torch.tensor([1 if parity_failed else 0], device=device)
+        dist.broadcast(flag, 0)
+        parity_failed = bool(int(flag.item()))
+    if parity_failed:
+        if rank == 0:
             print(json.dumps({"error": "parity check against oracle/_ref failed", "parity_check": line["parity_check"]}),
                   flush=True)
-            return 1
-    if distributed:
-        dist.barrier()
+        return 1
 
     phase("end-to-end leg")
     # ---- end to end through the public API with HOST buffers ------------------------------------
